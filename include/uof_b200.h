@@ -1,0 +1,159 @@
+/*
+ * uof_b200.h — C ABI of the B200-native Model_flow hot path (libuof_b200.so).
+ *
+ * Drop-in boundary for jianfenglihg/UnOpticalFlow's operator seams under core/networks
+ * (SURVEY.md section 8b).  The reference has no FFI: its seams are Python callables
+ * (`PWC_tf.corr`, `warp_flow`, `SSIM`, `Model_flow.compute_*`).  Each entry point below
+ * replaces the ATen op chain behind one of them; the reference file:line it replaces is
+ * cited per function.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise;
+ *   - tensors are dense NCHW (the reference's layout) unless a `channels_last` flag or an
+ *     explicit stride argument says otherwise;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; it is safe to capture the calls into a CUDA graph;
+ *   - return value: 0 = ok, UOF_ERR_* otherwise; uof_last_error() gives a message;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef UOF_B200_H
+#define UOF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UOF_OK 0
+#define UOF_ERR_INVALID_ARGUMENT 1
+#define UOF_ERR_CUDA 2
+#define UOF_ERR_UNSUPPORTED 3
+
+#define UOF_MAX_LEVELS 4
+#define UOF_NUM_DISPLACEMENTS 81   /* (2*4+1)^2, pwc_tf.py:16,97 */
+
+typedef void* uof_stream_t;        /* cudaStream_t */
+
+/* library / diagnostics --------------------------------------------------------------- */
+int uof_abi_version(void);
+const char* uof_last_error(void);
+/* number of kernel launches (incl. memsets) this library has enqueued since load */
+long long uof_launch_count(void);
+
+/* a1: cost volume.  Replaces PWC_tf.corr_naive (pwc_tf.py:97-106):
+ *   out[b, 9*i+j, y, x] = (1/C) * sum_c f1[b,c,y,x] * f2[b,c,y+i-4,x+j-4]   (zero outside)
+ * f1,f2: (B,C,H,W).  out: (B,81,H,W) with batch stride `out_batch_stride` elements
+ * (81*H*W when dense; larger when writing into a pre-allocated concat buffer). */
+int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
+                        int B, int C, int H, int W, long long out_batch_stride,
+                        uof_stream_t stream);
+/* backward of the above: gf1,gf2 (B,C,H,W) are fully overwritten. */
+int uof_cost_volume_bwd(const float* gout, long long gout_batch_stride,
+                        const float* f1, const float* f2, float* gf1, float* gf2,
+                        int B, int C, int H, int W, uof_stream_t stream);
+
+/* a2/a3: bilinear backward warp.  Replaces warp_flow (net_utils.py:16-54): mesh grid,
+ * normalisation, grid_sample(zeros padding) and, with use_mask, the validity mask
+ * (sum of in-bounds corner weights >= 0.9999, net_utils.py:47-52) in ONE kernel.
+ * x,out: (B,C,H,W) NCHW, or NHWC storage when channels_last != 0 (C % 4 == 0 required);
+ * flow: (B,2,H,W) NCHW always.  align_corners selects the grid_sample convention
+ * (0 = installed torch default, 1 = torch-1.2 behaviour). */
+int uof_warp_fwd(const float* x, const float* flow, float* out,
+                 int B, int C, int H, int W, int use_mask, int align_corners,
+                 int channels_last, uof_stream_t stream);
+/* gx may be NULL (image warps: x carries no gradient).  gx is zero-filled here and then
+ * accumulated with fp32 atomics; gflow (B,2,H,W) is overwritten. */
+int uof_warp_bwd(const float* gout, const float* x, const float* flow, float* gx, float* gflow,
+                 int B, int C, int H, int W, int use_mask, int align_corners,
+                 int channels_last, uof_stream_t stream);
+
+/* a4+a5+a6 fused: photometric weights + masked L1 + masked SSIM for BOTH directions, all
+ * pyramid levels in one launch.  Replaces Model_flow.compute_diff_weight (:101-134),
+ * compute_loss_with_mask x2 (:90-99, :241-242), compute_loss_ssim x2 (:137-148, :244-245)
+ * and SSIM (pytorch_ssim/ssim.py:4-19).   "l" = warped from the left image (reference
+ * "bwd"), "r" = from the right image (reference "fwd"). */
+typedef struct {
+  const float* img;        /* (B,3,H,W) target image at this level            */
+  const float* warped_l;   /* (B,3,H,W) masked warp of the left image          */
+  const float* warped_r;   /* (B,3,H,W) masked warp of the right image         */
+  float* weight_l;         /* (B,1,H,W) out: soft weight map, or NULL          */
+  float* weight_r;
+  float* diff_l;           /* (B,1,H,W) out: mean_c |img - warped|, or NULL    */
+  float* diff_r;
+  float* gwarped_l;        /* (B,3,H,W) out of the backward pass               */
+  float* gwarped_r;
+  int H, W;
+} uof_photo_level;
+/* sums: (nlevels,B,6) workspace, zero-filled here, then
+ *   [0]=sum d_l*w_l [1]=sum w_l [2]=sum d_r*w_r [3]=sum w_r [4]=sum ssim_term_l [5]=sum ssim_term_r
+ * loss_pixel, loss_ssim: (B) out, summed over levels and both directions. */
+int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B,
+                       float* sums, float* loss_pixel, float* loss_ssim, uof_stream_t stream);
+int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, int B, const float* sums,
+                       const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream);
+
+/* a6 seam: SSIM map.  Replaces SSIM(x,y) (pytorch_ssim/ssim.py:4-19) on N = B*C planes. */
+int uof_ssim_fwd(const float* x, const float* y, float* out, int N, int H, int W, uof_stream_t stream);
+int uof_ssim_bwd(const float* gout, const float* x, const float* y, float* gx, float* gy,
+                 int N, int H, int W, uof_stream_t stream);
+
+/* a7: edge-aware second-order smoothness.  Replaces Model_flow.gradients/cal_grad2_error/
+ * compute_loss_flow_smooth (model_flow_paper.py:152-177).  flow: (B,2,H,W) in pixels (the /20
+ * is applied inside); img: (Bimg,3,H,W), sample b reads image b % Bimg so both flow
+ * directions can share one launch. */
+typedef struct {
+  const float* flow;
+  const float* img;
+  float* gflow;            /* (B,2,H,W) out of the backward pass */
+  int H, W;
+} uof_smooth_level;
+int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
+                        float* sums /* (nlevels,B,2) */, float* loss /* (B) */, uof_stream_t stream);
+int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
+                        const float* g_loss, uof_stream_t stream);
+
+/* a8: flow-direction consistency.  Replaces get_flow_normalization + compute_loss_flow_consis
+ * (model_flow_paper.py:44-51,180-195).  Gradient flows to flow_fwd only. */
+typedef struct {
+  const float* flow_fwd;   /* (B,2,H,W) */
+  const float* flow_bwd;   /* (B,2,H,W) */
+  const float* weight_fwd; /* (B,1,H,W) */
+  float* gflow_fwd;        /* (B,2,H,W) out of the backward pass */
+  int H, W;
+} uof_consis_level;
+int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, int B,
+                        float* sums /* (nlevels,B,2) */, float* loss /* (B) */, uof_stream_t stream);
+int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, const float* sums,
+                        const float* g_loss, uof_stream_t stream);
+
+/* a9: image pyramid.  Replaces Model_flow.generate_img_pyramid (model_flow_paper.py:54-60) for
+ * levels 1..nlevels-1 (level 0 is the input itself); adaptive_avg_pool2d bin rule
+ * [floor(i*H/h), ceil((i+1)*H/h)).  img is addressed with explicit element strides so the
+ * vertically stacked triplet (B,3,3H,W) can be read in place. */
+int uof_img_pyramid(const float* img, long long stride_b, long long stride_c, long long stride_h,
+                    float* const* outs /* host array of nlevels-1 device pointers */, int nlevels,
+                    int B, int C, int H, int W, uof_stream_t stream);
+
+/* a12: forward splat ("transformerFwd").  NOT in the reference.
+ * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;
+ * out: (B,H,W,C), zero-filled here then accumulated with warp-aggregated fp32 atomics. */
+int uof_splat_fwd(const float* u, const float* flow, float* out,
+                  int B, int H, int W, int C, uof_stream_t stream);
+/* gu (nullable) and gflow (nullable) are gathers from gout: no atomics. */
+int uof_splat_bwd(const float* gout, const float* u, const float* flow, float* gu, float* gflow,
+                  int B, int H, int W, int C, uof_stream_t stream);
+/* integer contract: idx (B,H,W,4) int64 flat target indices b*H*W + yc*W + xc in corner order
+ * (x0,y0),(x0,y1),(x1,y0),(x1,y1); -1 where the corner is out of bounds. */
+int uof_splat_targets(const float* flow, long long* idx, int B, int H, int W, uof_stream_t stream);
+/* visibility = clamp(range_map, 0, 1), in place on `range` (B*H*W elements). */
+int uof_clamp01(float* range, long long n, uof_stream_t stream);
+
+/* a13: forward-backward consistency mask.  NOT in the reference (App. D).
+ * flows (B,2,H,W); mask (B,1,H,W) = |f_fwd + warp(f_rev, f_fwd)|_2 < max(alpha, beta*|f_fwd|_2). */
+int uof_fb_consistency_mask(const float* flow_fwd, const float* flow_rev, float* mask,
+                            int B, int H, int W, float alpha, float beta, int align_corners,
+                            uof_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UOF_B200_H */

@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library loads and exports every symbol include/uof_b200.h declares (no compute calls),
+and the host-side mirror of the reference interface behaves (names, keys, error behaviour)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'uof_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(uof_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from unopticalflow_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from unopticalflow_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), 'libuof_b200.so does not export %s' % s
+        assert s in _lib.SIGNATURES or s in _lib.DIAGNOSTICS, 'no ctypes signature for %s' % s
+    assert set(_lib.SIGNATURES) | set(_lib.DIAGNOSTICS) == set(syms)
+    assert lib.uof_abi_version() == 1
+
+
+def test_argument_validation_without_gpu(lib):
+    """Invalid arguments are rejected before any CUDA call, with a message."""
+    from unopticalflow_b200 import _lib
+    with pytest.raises(ValueError, match='null pointer'):
+        _lib.call('uof_cost_volume_fwd', None, None, None, 1, 1, 1, 1, 81, None)
+    with pytest.raises(ValueError, match='bad shape'):
+        _lib.call('uof_warp_fwd', ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 0, 3, 4, 4, 0, 0, 0, None)
+    with pytest.raises(ValueError, match='channels_last'):
+        _lib.call('uof_warp_fwd', ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 3, 4, 4, 0, 0, 1, None)
+    with pytest.raises(ValueError, match='nlevels'):
+        _lib.call('uof_photo_loss_fwd', None, 0, 1, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), None)
+
+
+def test_library_missing_fails_loudly(tmp_path, monkeypatch):
+    from unopticalflow_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    with pytest.raises(_lib.LibraryMissing, match='no CPU or PyTorch fallback'):
+        _lib.load(str(tmp_path / 'nope.so'))
+
+
+def test_no_cpu_fallback():
+    import unopticalflow_b200 as u
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        u.corr(x, x)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        u.warp_flow(x, torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        u.SSIM(x, x)
+
+
+def test_warp_flow_shape_error_matches_reference():
+    import unopticalflow_b200 as u
+    with pytest.raises(ValueError, match='the shape of grid .* is not equal to the shape of flow'):
+        u.warp_flow(torch.zeros(1, 3, 12, 39), torch.zeros(1, 2, 12, 40))      # SURVEY F6 case
+
+
+def test_model_surface_and_state_dict_keys():
+    import unopticalflow_b200 as u
+    from oracle import model as omodel
+    from util import load_golden
+    torch.manual_seed(0)
+    m = u.get_model('flow')(omodel.Cfg)
+    torch.manual_seed(0)
+    o = omodel.Model_flow(omodel.Cfg)
+    sd, so = m.state_dict(), o.state_dict()
+    assert list(sd.keys()) == list(so.keys()) == [str(k) for k in load_golden('step_b1_64x128.npz')['param_keys']]
+    assert len(sd) == 98 and sum(p.numel() for p in m.parameters()) == 5134324
+    assert all(torch.equal(sd[k], so[k]) for k in sd), 'same seed -> same init as the reference'
+    for name in ('forward', 'inference_flow', 'generate_img_pyramid', 'warp_flow_pyramid', 'compute_diff_weight',
+                 'compute_loss_with_mask', 'compute_loss_ssim', 'compute_loss_flow_smooth', 'compute_loss_flow_consis',
+                 'get_flow_normalization'):
+        assert callable(getattr(m, name))
+    assert m.pwc_model.corr is not None and callable(m.pwc_model.warp)
+    with pytest.raises(ValueError, match='Mode depth not found'):
+        u.get_model('depth')
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under unopticalflow_b200/ may import it."""
+    pkg = os.path.join(ROOT, 'unopticalflow_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(dirpath, f)

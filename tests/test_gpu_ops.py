@@ -1,0 +1,397 @@
+"""GPU parity tests: every CUDA operator (called through the C ABI via unopticalflow_b200.ops) against the
+CPU oracle on the same seeded inputs, against the golden fixtures produced by the unmodified reference,
+and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (north star): values and gradients within 1e-4 relative (max-abs error over max-abs reference,
+FP32); integer splat targets bit-exact; thresholded masks >= 99.9 % pixel agreement.
+"""
+import pytest
+import torch
+
+from oracle import ops as O
+from util import MASK_AGREE, REL_TOL, assert_close, flows_like, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def U(cuda):
+    import unopticalflow_b200 as u
+    from unopticalflow_b200 import _lib
+    _lib.load()
+    return u
+
+
+def gpu(t, grad=False):
+    return t.detach().cuda().requires_grad_(grad)
+
+
+# ------------------------------------------------------------------------------------------ a1
+LEVEL_SHAPES = [(2, 196, 4, 13), (2, 128, 8, 26), (2, 96, 16, 52), (2, 64, 32, 104), (2, 32, 64, 208)]
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 6, 9), (1, 5, 11, 7), (1, 3, 1, 1), (3, 17, 33, 70)] + LEVEL_SHAPES)
+def test_cost_volume_vs_oracle(U, shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    B, C, H, W = shape
+    f1 = torch.randn(shape, generator=g, requires_grad=True)
+    f2 = torch.randn(shape, generator=g, requires_grad=True)
+    ct = torch.randn(B, 81, H, W, generator=g)
+    ref = O.cost_volume(f1, f2)
+    r1, r2 = torch.autograd.grad((ref * ct).sum(), (f1, f2))
+    a, b = gpu(f1, True), gpu(f2, True)
+    out = U.corr(a, b)
+    assert out.shape == (B, 81, H, W)
+    g1, g2 = torch.autograd.grad((out * ct.cuda()).sum(), (a, b))
+    assert_close(out, ref, REL_TOL, 'corr fwd')
+    assert_close(g1, r1, REL_TOL, 'corr grad f1')
+    assert_close(g2, r2, REL_TOL, 'corr grad f2')
+
+
+def test_cost_volume_golden(U):
+    for tag in ('small', 'odd'):
+        g = load_golden('corr_%s.npz' % tag)
+        a, b = gpu(g['f1'], True), gpu(g['f2'], True)
+        out = U.corr(a, b)
+        g1, g2 = torch.autograd.grad((out * g['ct'].cuda()).sum(), (a, b))
+        assert_close(out, g['out'], REL_TOL)
+        assert_close(g1, g['g1'], REL_TOL)
+        assert_close(g2, g['g2'], REL_TOL)
+
+
+def test_cost_volume_full_size_properties(U):
+    """B=8 level-2 shape of the 256x832 config: centre displacement == channel mean of products,
+    shifted displacement == shifted product, linearity, and <gout, corr(f1,f2)> == <gf1, f1> (Euler)."""
+    g = torch.Generator(device='cuda').manual_seed(7)
+    f1 = torch.randn(8, 32, 64, 208, device='cuda', generator=g, requires_grad=True)
+    f2 = torch.randn(8, 32, 64, 208, device='cuda', generator=g, requires_grad=True)
+    out = U.corr(f1, f2)
+    assert_close(out[:, 40], (f1 * f2).mean(1), 1e-5, 'centre displacement')
+    i, j = 1, 7     # dy = -3, dx = +3
+    ref = torch.zeros(8, 64, 208, device='cuda')
+    ref[:, 3:, :-3] = (f1[:, :, 3:, :-3] * f2[:, :, :-3, 3:]).mean(1)
+    assert_close(out[:, 9 * i + j], ref, 1e-5, 'shifted displacement')
+    assert_close(U.corr(2.5 * f1.detach(), f2.detach()), 2.5 * out, 1e-5, 'linearity')
+    ct = torch.randn(out.shape, device='cuda', generator=g)
+    g1, g2 = torch.autograd.grad((out * ct).sum(), (f1, f2))
+    s = float((out * ct).sum())
+    assert abs(float((g1 * f1).sum()) - s) <= 1e-3 * abs(s) + 1e-2      # bilinear form: <g1,f1> = <g2,f2> = <ct,out>
+    assert abs(float((g2 * f2).sum()) - s) <= 1e-3 * abs(s) + 1e-2
+
+
+# --------------------------------------------------------------------------------------- a2/a3
+@pytest.mark.parametrize('ac', [False, True])
+@pytest.mark.parametrize('use_mask', [False, True])
+@pytest.mark.parametrize('shape,sigma', [((2, 4, 12, 16), 3.0), ((2, 3, 10, 14), 0.7), ((1, 3, 9, 13), 20.0),
+                                         ((2, 32, 33, 47), 2.0), ((1, 1, 1, 5), 1.0)])
+def test_warp_vs_oracle(U, shape, sigma, use_mask, ac):
+    g = torch.Generator().manual_seed(11 + sum(shape))
+    B, C, H, W = shape
+    x = torch.rand(shape, generator=g, requires_grad=True)
+    fl = flows_like(g, B, H, W, sigma).requires_grad_(True)
+    ct = torch.randn(shape, generator=g)
+    ref = O.warp_flow(x, fl, use_mask=use_mask, align_corners=ac)
+    rx, rf = torch.autograd.grad((ref * ct).sum(), (x, fl))
+    a, f = gpu(x, True), gpu(fl, True)
+    out = U.warp_flow(a, f, use_mask=use_mask, align_corners=ac)
+    gx, gf = torch.autograd.grad((out * ct.cuda()).sum(), (a, f))
+    assert_close(out, ref, REL_TOL, 'warp fwd')
+    assert_close(gx, rx, REL_TOL, 'warp grad x')
+    assert_close(gf, rf, REL_TOL, 'warp grad flow')
+
+
+def test_warp_golden(U):
+    for tag in ('feat', 'img', 'wild'):
+        for ac in (0, 1):
+            for m in (0, 1):
+                g = load_golden('warp_%s_ac%d_m%d.npz' % (tag, ac, m))
+                a, f = gpu(g['x'], True), gpu(g['flow'], True)
+                out = U.warp_flow(a, f, use_mask=bool(m), align_corners=bool(ac))
+                gx, gf = torch.autograd.grad((out * g['ct'].cuda()).sum(), (a, f))
+                assert_close(out, g['out'], REL_TOL)
+                assert_close(gx, g['gx'], REL_TOL)
+                assert_close(gf, g['gflow'], REL_TOL)
+    s = load_golden('warp_smoke.npz')      # the reference's own __main__ input (net_utils.py:56-60)
+    x = torch.ones(1, 1, 10, 10, device='cuda')
+    fl = torch.stack([torch.full((1, 10, 10), 3.0), torch.zeros(1, 10, 10)], 1).cuda()
+    assert_close(U.warp_flow(x, fl), s['y_ac0'], 1e-6)
+    assert_close(U.warp_flow(x, fl, align_corners=True), s['y_ac1'], 1e-6)
+
+
+def test_warp_channels_last_matches_nchw(U):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 20, 28, generator=g)
+    fl = flows_like(g, 2, 20, 28, 2.5)
+    ct = torch.randn(2, 32, 20, 28, generator=g).cuda()
+    a, f = gpu(x, True), gpu(fl, True)
+    out = U.warp_flow(a, f)
+    gx, gf = torch.autograd.grad((out * ct).sum(), (a, f))
+    a2 = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    f2 = gpu(fl, True)
+    out2 = U.warp_flow(a2, f2)
+    assert out2.is_contiguous(memory_format=torch.channels_last)
+    gx2, gf2 = torch.autograd.grad((out2 * ct).sum(), (a2, f2))
+    assert_close(out2, out, 1e-6)
+    assert_close(gx2, gx, 1e-5)
+    assert_close(gf2, gf, 1e-5)
+
+
+def test_warp_zero_flow_full_size(U):
+    """zero flow at 256x832 with use_mask masks exactly the 1-px border ring
+    (align_corners=False) and is the identity with align_corners=True."""
+    x = torch.rand(2, 3, 256, 832, device='cuda') + 0.5
+    z = torch.zeros(2, 2, 256, 832, device='cuda')
+    out = U.warp_flow(x, z, use_mask=True)
+    valid = (out != 0).all(1)
+    assert int(valid.sum()) == 2 * 254 * 830
+    assert bool(valid[:, 1:-1, 1:-1].all())
+    ident = U.warp_flow(x, z, use_mask=True, align_corners=True)
+    assert_close(ident, x, 1e-6)
+
+
+def test_warp_mask_agreement_full_size(U):
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 3, 256, 832, generator=g) + 0.25
+    fl = torch.randn(1, 2, 256, 832, generator=g) * 6
+    ref = (O.warp_flow(x, fl, use_mask=True) != 0).all(1)
+    out = (U.warp_flow(x.cuda(), fl.cuda(), use_mask=True) != 0).all(1).cpu()
+    assert float((ref == out).float().mean()) >= MASK_AGREE
+
+
+# ------------------------------------------------------------------------------------------ a6
+@pytest.mark.parametrize('shape', [(2, 3, 12, 16), (1, 3, 33, 61), (1, 1, 5, 70), (2, 2, 3, 3)])
+def test_ssim_vs_oracle(U, shape):
+    g = torch.Generator().manual_seed(2 + sum(shape))
+    x = torch.rand(shape, generator=g, requires_grad=True)
+    y = torch.rand(shape, generator=g, requires_grad=True)
+    ct = torch.randn(shape, generator=g)
+    ref = O.ssim(x, y)
+    rx, ry = torch.autograd.grad((ref * ct).sum(), (x, y))
+    a, b = gpu(x, True), gpu(y, True)
+    out = U.SSIM(a, b)
+    gx, gy = torch.autograd.grad((out * ct.cuda()).sum(), (a, b))
+    assert_close(out, ref, REL_TOL, 'ssim')
+    assert_close(gx, rx, REL_TOL, 'ssim grad x')
+    assert_close(gy, ry, REL_TOL, 'ssim grad y')
+
+
+def test_ssim_golden_and_identity(U):
+    g = load_golden('ssim.npz')
+    a, b = gpu(g['x'], True), gpu(g['y'], True)
+    out = U.SSIM(a, b)
+    gx, gy = torch.autograd.grad((out * g['ct'].cuda()).sum(), (a, b))
+    assert_close(out, g['out'], REL_TOL)
+    assert_close(gx, g['gx'], REL_TOL)
+    assert_close(gy, g['gy'], REL_TOL)
+    x = torch.rand(8, 3, 256, 832, device='cuda')
+    s = U.SSIM(x, x)
+    assert float((s - 1).abs().max()) < 1e-4        # SSIM(x, x) == 1
+
+
+# ------------------------------------------------------------------------------------ a4+a5+a6
+def pyramid_case(g, B, H, W, S=3, sigma=1.5):
+    imgs = [torch.rand(B, 3, H, W, generator=g) for _ in range(3)]
+    pyr = [O.img_pyramid(i, S) for i in imgs]
+    fb = [flows_like(g, B, H >> s, W >> s, sigma / (s + 1), oob=(s == 0)) for s in range(S)]
+    ff = [flows_like(g, B, H >> s, W >> s, sigma / (s + 1), oob=False) for s in range(S)]
+    from_l = [O.warp_flow(pyr[0][s], fb[s], use_mask=True) for s in range(S)]
+    from_r = [O.warp_flow(pyr[2][s], ff[s], use_mask=True) for s in range(S)]
+    return pyr, fb, ff, from_l, from_r
+
+
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 40, 72), (3, 16, 30)])
+def test_photometric_fused_vs_oracle(U, B, H, W):
+    g = torch.Generator().manual_seed(B * 100 + H)
+    S = 3
+    pyr, _, _, from_l, from_r = pyramid_case(g, B, H, W, S)
+    wl = [t.clone().requires_grad_(True) for t in from_l]
+    wr = [t.clone().requires_grad_(True) for t in from_r]
+    d_b, d_f, w_b, w_f = O.diff_weight(wl, pyr[1], wr, S)
+    ref_pix = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+    ref_ssim = O.loss_ssim(pyr[1], wr, w_f, S) + O.loss_ssim(pyr[1], wl, w_b, S)
+    ct = torch.randn(2, B, generator=g)
+    ref_g = torch.autograd.grad((ref_pix * ct[0]).sum() + (ref_ssim * ct[1]).sum(), wl + wr)
+
+    cl = [gpu(t, True) for t in from_l]
+    cr = [gpu(t, True) for t in from_r]
+    ci = [t.cuda() for t in pyr[1]]
+    pix, ssim, gw_b, gw_f, gd_b, gd_f = U.ops.photometric_losses(ci, cl, cr, S, return_diffs=True)
+    got_g = torch.autograd.grad((pix * ct[0].cuda()).sum() + (ssim * ct[1].cuda()).sum(), cl + cr)
+    assert_close(pix, ref_pix, REL_TOL, 'loss_pixel')
+    assert_close(ssim, ref_ssim, REL_TOL, 'loss_ssim')
+    for s in range(S):
+        assert_close(gw_b[s], w_b[s], REL_TOL, 'weight_bwd')
+        assert_close(gw_f[s], w_f[s], REL_TOL, 'weight_fwd')
+        assert_close(gd_b[s], d_b[s], REL_TOL, 'diff_bwd')
+        assert_close(gd_f[s], d_f[s], REL_TOL, 'diff_fwd')
+    for a, b in zip(got_g, ref_g):
+        assert_close(a, b, REL_TOL, 'd loss / d warped')
+
+    # stacked [left;right] entry point used by Model_flow.forward gives the same numbers
+    both = [torch.cat((from_l[s], from_r[s]), 0).cuda().requires_grad_(True) for s in range(S)]
+    pix2, ssim2, _, _ = U.ops.photometric_losses_stacked(ci, both, S)
+    g2 = torch.autograd.grad((pix2 * ct[0].cuda()).sum() + (ssim2 * ct[1].cuda()).sum(), both)
+    assert_close(pix2, pix, 1e-6)
+    assert_close(ssim2, ssim, 1e-6)
+    for s in range(S):
+        assert_close(g2[s], torch.cat((got_g[s], got_g[S + s]), 0), 1e-5)
+
+
+# --------------------------------------------------------------------------------------- a7/a8
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 24, 66), (2, 8, 12)])
+def test_smooth_and_consis_vs_oracle(U, B, H, W):
+    g = torch.Generator().manual_seed(B + H + W)
+    S = 3 if H >= 16 else 2
+    pyr, fb, ff, from_l, from_r = pyramid_case(g, B, H, W, S)
+    _, _, _, w_f = O.diff_weight(from_l, pyr[1], from_r, S)
+    fb = [t.requires_grad_(True) for t in fb]
+    ff = [t.requires_grad_(True) for t in ff]
+    ct = torch.randn(3, B, generator=g)
+    r_sf, r_sb = O.loss_flow_smooth(ff, pyr[1], S), O.loss_flow_smooth(fb, pyr[1], S)
+    r_c = O.loss_flow_consis(ff, fb, w_f, S)
+    ref_g = torch.autograd.grad((r_sf * ct[0]).sum() + (r_sb * ct[1]).sum() + (r_c * ct[2]).sum(), ff + fb, allow_unused=True)
+
+    cff, cfb = [gpu(t, True) for t in ff], [gpu(t, True) for t in fb]
+    ci, cw = [t.cuda() for t in pyr[1]], [t.cuda() for t in w_f]
+    sf, sb = U.ops.flow_smooth_loss(cff, ci, S), U.ops.flow_smooth_loss(cfb, ci, S)
+    c = U.ops.flow_consis_loss(cff, cfb, cw, S)
+    got = torch.autograd.grad((sf * ct[0].cuda()).sum() + (sb * ct[1].cuda()).sum() + (c * ct[2].cuda()).sum(), cff + cfb,
+                              allow_unused=True)
+    assert_close(sf, r_sf, REL_TOL, 'smooth fwd')
+    assert_close(sb, r_sb, REL_TOL, 'smooth bwd')
+    assert_close(c, r_c, REL_TOL, 'consis')
+    for a, b in zip(got, ref_g):
+        assert_close(a, b, REL_TOL, 'd loss / d flow')
+
+    # both directions in one launch: flow batch 2B against image batch B
+    both = [torch.cat((b_, f_), 0).detach().cuda().requires_grad_(True) for b_, f_ in zip(fb, ff)]
+    s2 = U.ops.flow_smooth_loss(both, ci, S)
+    assert_close(s2[:B], sb, 1e-6)
+    assert_close(s2[B:], sf, 1e-6)
+
+
+def test_losses_golden_from_reference(U):
+    """Inputs and outputs recorded from the unmodified reference (tests/golden/losses.npz): warp with mask,
+    weights, all four losses and their flow gradients through the CUDA path."""
+    g = load_golden('losses.npz')
+    S = 3
+    pyr = [U.ops.img_pyramid(g[k].cuda(), 4) for k in ('imgl', 'img', 'imgr')]
+    fb = [gpu(g['fb%d' % s], True) for s in range(4)]
+    ff = [gpu(g['ff%d' % s], True) for s in range(4)]
+    from_l = [U.warp_flow(pyr[0][s], fb[s], use_mask=True) for s in range(S)]
+    from_r = [U.warp_flow(pyr[2][s], ff[s], use_mask=True) for s in range(S)]
+    pix, ssim, w_b, w_f = U.ops.photometric_losses(pyr[1], from_l, from_r, S)
+    smooth = U.ops.flow_smooth_loss(ff, pyr[1], S) + U.ops.flow_smooth_loss(fb, pyr[1], S)
+    consis = U.ops.flow_consis_loss(ff, fb, w_f, S)
+    pack = [pix, ssim, smooth, consis]
+    total = sum((p * c.cuda()).sum() for p, c in zip(pack, g['cts']))
+    grads = torch.autograd.grad(total, fb[:3] + ff[:3])
+    for k, name in enumerate(('loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis')):
+        assert_close(pack[k], g[name], REL_TOL, name)
+    for s in range(3):
+        assert_close(w_b[s], g['wb%d' % s], REL_TOL)
+        assert_close(w_f[s], g['wf%d' % s], REL_TOL)
+        assert_close(grads[s], g['gfb%d' % s], REL_TOL, 'grad flow bwd %d' % s)
+        assert_close(grads[3 + s], g['gff%d' % s], REL_TOL, 'grad flow fwd %d' % s)
+
+
+def test_model_method_api(U):
+    """compute_* methods keep the reference's list-in / (B,) out contract and values."""
+    from oracle.model import Cfg
+    g = torch.Generator().manual_seed(21)
+    B, H, W, S = 2, 32, 48, 3
+    pyr, fb, ff, from_l, from_r = pyramid_case(g, B, H, W, S)
+    d_b, d_f, w_b, w_f = O.diff_weight(from_l, pyr[1], from_r, S)
+    m = U.Model_flow(Cfg).cuda()
+    c = lambda ts: [t.cuda() for t in ts]
+    gd_b, gd_f, gw_b, gw_f = m.compute_diff_weight(c(from_l), c(pyr[1]), c(from_r))
+    for s in range(S):
+        assert_close(gd_b[s], d_b[s]); assert_close(gd_f[s], d_f[s])
+        assert_close(gw_b[s], w_b[s]); assert_close(gw_f[s], w_f[s])
+    assert_close(m.compute_loss_with_mask(gd_f, gw_f), O.loss_with_mask(d_f, w_f, S))
+    assert_close(m.compute_loss_ssim(c(pyr[1]), c(from_r), gw_f), O.loss_ssim(pyr[1], from_r, w_f, S))
+    assert_close(m.compute_loss_flow_smooth(c(ff), c(pyr[1])), O.loss_flow_smooth(ff, pyr[1], S))
+    assert_close(m.compute_loss_flow_consis(c(ff), c(fb), gw_f), O.loss_flow_consis(ff, fb, w_f, S))
+    wp = m.warp_flow_pyramid(c(pyr[0]), c(fb))
+    for s in range(S):
+        assert_close(wp[s], from_l[s])
+
+
+# ------------------------------------------------------------------------------------------ a9
+@pytest.mark.parametrize('shape', [(2, 3, 64, 128), (1, 3, 37, 50), (8, 3, 256, 832)])
+def test_img_pyramid(U, shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(shape, generator=g)
+    ref = O.img_pyramid(x, 4)
+    out = U.ops.img_pyramid(x.cuda(), 4)
+    for a, b in zip(out, ref):
+        assert a.shape == b.shape
+        assert_close(a, b, 1e-5)
+    # strided view of a stacked triplet is read in place
+    B, C, H, W = shape
+    trip = torch.rand(B, C, 3 * H, W, generator=g)
+    out2 = U.ops.img_pyramid(trip.cuda()[:, :, H:2 * H], 3)
+    for a, b in zip(out2, O.img_pyramid(trip[:, :, H:2 * H], 3)):
+        assert_close(a, b, 1e-5)
+
+
+# -------------------------------------------------------------------------------------- a12/a13
+@pytest.mark.parametrize('B,H,W,sigma', [(2, 9, 11, 2.0), (1, 32, 50, 8.0), (2, 64, 208, 1.0)])
+def test_splat_targets_bit_exact_and_range_map(U, B, H, W, sigma):
+    g = torch.Generator().manual_seed(B + H + W)
+    flow = torch.randn(B, H, W, 2, generator=g) * sigma
+    flow[:, :, -1, 0] += W           # out of bounds column
+    flow[0, 0, :, :] = 0.0           # exactly integral coordinates
+    idx, inb, wts = O.splat_targets(flow)
+    got = U.ops.splat_targets(flow.cuda()).cpu()
+    assert torch.equal(got, idx), 'splat target indices must be bit-exact'
+    r_ref = O.range_map(flow)
+    r = U.ops.range_map(flow.cuda())
+    assert_close(r, r_ref, REL_TOL, 'range map')
+    agree = ((r.cpu() > 0.5) == (r_ref > 0.5)).float().mean()
+    assert float(agree) >= MASK_AGREE
+    occ = U.ops.occlusion_mask(flow.cuda())
+    assert_close(occ, r_ref.clamp(0, 1), REL_TOL)
+
+
+@pytest.mark.parametrize('C', [1, 3, 8])
+def test_splat_values_and_grads(U, C):
+    g = torch.Generator().manual_seed(40 + C)
+    B, H, W = 2, 12, 17
+    u = torch.rand(B, H, W, C, generator=g, requires_grad=True)
+    flow = (torch.randn(B, H, W, 2, generator=g) * 2).requires_grad_(True)
+    ct = torch.randn(B, H, W, C, generator=g)
+    ref = O.splat(u, flow)
+    ru, rf = torch.autograd.grad((ref * ct).sum(), (u, flow))
+    a, f = gpu(u, True), gpu(flow, True)
+    out = U.ops.transformerFwd(a, f, [H, W])
+    gu, gf = torch.autograd.grad((out * ct.cuda()).sum(), (a, f))
+    assert_close(out, ref, REL_TOL, 'splat fwd')
+    assert_close(gu, ru, REL_TOL, 'splat grad u')
+    assert_close(gf, rf, REL_TOL, 'splat grad flow')
+
+
+def test_range_map_full_size_mass(U):
+    """256x832 B=8: splatted mass equals the sum of in-bounds corner weights; zero flow gives all ones."""
+    flow = torch.randn(8, 256, 832, 2, device='cuda') * 3
+    r = U.ops.range_map(flow)
+    idx = U.ops.splat_targets(flow)
+    assert int((idx >= 0).sum()) > 0
+    # every source pixel distributes weight 1 unless corners fall outside
+    assert float(r.sum()) <= 8 * 256 * 832 * (1 + 1e-5)
+    assert float(r.sum()) >= 0.97 * 8 * 256 * 832
+    ones = U.ops.range_map(torch.zeros(1, 256, 832, 2, device='cuda'))
+    assert float((ones - 1).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('ac', [False, True])
+def test_fb_consistency_mask(U, ac):
+    g = torch.Generator().manual_seed(77)
+    B, H, W = 2, 40, 64
+    f = torch.randn(B, 2, H, W, generator=g) * 4
+    r = -f + torch.randn(B, 2, H, W, generator=g) * 2.5
+    ref = O.fb_consistency_mask(f, r, 3.0, 0.05, align_corners=ac)
+    out = U.ops.fb_consistency_mask(f.cuda(), r.cuda(), 3.0, 0.05, align_corners=ac).cpu()
+    assert out.shape == (B, 1, H, W)
+    assert 0.05 < float(ref.mean()) < 0.95
+    assert float((out == ref).float().mean()) >= MASK_AGREE

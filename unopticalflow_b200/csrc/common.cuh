@@ -1,0 +1,115 @@
+// Shared device/host helpers for libuof_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/uof_b200.h"
+
+namespace uof {
+
+constexpr int kNumSMs = 148;            // B200: 2 dies x 74 SMs
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);
+
+#define UOF_REQUIRE(cond, ...)                     \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::uof::set_error(__VA_ARGS__);               \
+      return UOF_ERR_INVALID_ARGUMENT;             \
+    }                                              \
+  } while (0)
+
+#define UOF_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      ::uof::set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return UOF_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- warp-level reductions --------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// ---- streaming loads/stores -------------------------------------------------------------------
+__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
+
+// ---- cp.async (LDGSTS) with zero fill ---------------------------------------------------------
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src, bool valid) {
+  unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  int bytes = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src, bool valid) {
+  unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- bilinear sampling coordinates of warp_flow (net_utils.py:39-46 + ATen grid_sampler) ---------
+// Same fp32 operation order as the reference so that floor() lands on the same integer:
+//   v = x + fx;  g = 2*v/max(W-1,1) - 1;  ix = ((g+1)*W - 1)/2        (align_corners = False)
+//                                          ix = (g+1)/2*(W-1)          (align_corners = True)
+// __f*_rn intrinsics keep ptxas from contracting the chain into FMAs.
+__device__ __forceinline__ float sample_coord(float pos, float f, int size, bool align_corners) {
+  float v = __fadd_rn(pos, f);
+  float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)max(size - 1, 1)), 1.0f);
+  if (align_corners) return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
+  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 2.0f);
+}
+// d(ix)/d(flow) for the mapping above.
+inline float coord_scale(int size, bool align_corners) {
+  float dg = 2.0f / (float)(size - 1 > 1 ? size - 1 : 1);
+  return align_corners ? dg * 0.5f * (float)(size - 1) : dg * 0.5f * (float)size;
+}
+
+struct Bilinear {
+  int x0, y0;            // top-left corner (may be out of range)
+  float w00, w01, w10, w11;   // weights for (y0,x0) (y0,x1) (y1,x0) (y1,x1), zeroed when the corner is out of bounds
+  float tx, ty;
+  bool in00, in01, in10, in11;
+};
+
+__device__ __forceinline__ Bilinear make_bilinear(float ix, float iy, int H, int W) {
+  Bilinear b;
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  b.tx = ix - fx0;
+  b.ty = iy - fy0;
+  // ATen forms the "one minus" weights as (x0 + 1) - ix, not 1 - tx
+  float ux = (fx0 + 1.0f) - ix, uy = (fy0 + 1.0f) - iy;
+  // clamp before the int conversion so that huge/NaN coordinates cannot overflow
+  fx0 = fminf(fmaxf(fx0, -2.0f), (float)W + 1.0f);
+  fy0 = fminf(fmaxf(fy0, -2.0f), (float)H + 1.0f);
+  b.x0 = (int)fx0;
+  b.y0 = (int)fy0;
+  bool xin0 = (b.x0 >= 0) && (b.x0 < W), xin1 = (b.x0 + 1 >= 0) && (b.x0 + 1 < W);
+  bool yin0 = (b.y0 >= 0) && (b.y0 < H), yin1 = (b.y0 + 1 >= 0) && (b.y0 + 1 < H);
+  b.in00 = xin0 && yin0;
+  b.in01 = xin1 && yin0;
+  b.in10 = xin0 && yin1;
+  b.in11 = xin1 && yin1;
+  b.w00 = b.in00 ? ux * uy : 0.0f;
+  b.w01 = b.in01 ? b.tx * uy : 0.0f;
+  b.w10 = b.in10 ? ux * b.ty : 0.0f;
+  b.w11 = b.in11 ? b.tx * b.ty : 0.0f;
+  return b;
+}
+
+}  // namespace uof

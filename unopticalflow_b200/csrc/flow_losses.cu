@@ -1,0 +1,363 @@
+// a7 + a8: edge-aware second-order smoothness and flow-direction consistency losses.
+// Replaces, in /root/reference/core/networks/model_flow_paper.py, gradients / cal_grad2_error /
+// compute_loss_flow_smooth (:152-177, 154 slice/sub launches per direction) and
+// get_flow_normalization / compute_loss_flow_consis (:44-51,180-195, 50 launches).
+//
+// Smoothness uses the marching-warp scheme (strips.cuh): a lane loads the 2 flow + 3 image values of
+// its pixel once per row, x-neighbours come from warp shuffles, y-neighbours from a 3-row register
+// ring; all pyramid levels and both flow directions (flow batch B, image batch Bimg, image index
+// b % Bimg) go in one launch.  Consistency is a pure streaming kernel.
+#include "strips.cuh"
+
+namespace uof {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr float kEps = 1e-12f;
+
+struct SmoothParams {
+  uof_smooth_level lv[UOF_MAX_LEVELS];
+  StripTable T;
+  int Bimg;
+};
+
+__device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+// exp(-10 * mean_c |a_c - b_c|)   (model_flow_paper.py:159-160)
+__device__ __forceinline__ float edge_weight(const float* a, const float* b) {
+  return expf(-10.0f * ((fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2])) / 3.0f));
+}
+
+// --------------------------------------------------------------------------------- smooth fwd
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Strip sc;
+  if (!locate_strip<1>(P.T, gw, lane, sc)) return;
+  const uof_smooth_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const float* fb = L.flow + (size_t)sc.b * 2 * plane;
+  const float* ib = L.img + (size_t)(sc.b % P.Bimg) * 3 * plane;
+  const bool col_in = sc.col >= 0 && sc.col < W;
+  const bool col_out = col_in && lane >= 1 && lane <= 30;
+
+  float f[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // flow/20 at rows r-2, r-1, r
+  float im[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};    // image at rows r-1, r
+  float sum_x = 0.0f, sum_y = 0.0f;
+
+  for (int r = sc.y0 - 1; r <= sc.y1; ++r) {
+    const bool inb = col_in && r >= 0 && r < H;
+    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      f[0][k] = f[1][k];
+      f[1][k] = f[2][k];
+      f[2][k] = inb ? __ldg(fb + off + k * plane) / 20.0f : 0.0f;   // :174 flow/20.0
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      im[0][c] = im[1][c];
+      im[1][c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
+    }
+    // x term centred on (r, col): needs col-1 and col+1 from the neighbouring lanes
+    float ir[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ir[c] = __shfl_down_sync(kFullMask, im[1][c], 1);
+    float d2x = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float fl = __shfl_up_sync(kFullMask, f[2][k], 1), fr = __shfl_down_sync(kFullMask, f[2][k], 1);
+      d2x += fabsf((fr - f[2][k]) - (f[2][k] - fl));   // :153-155,163-164
+    }
+    if (col_out && r >= sc.y0 && r < sc.y1 && sc.col >= 1 && sc.col <= W - 2) sum_x = fmaf(edge_weight(ir, im[1]), d2x, sum_x);
+    // y term centred on row m = r-1: rows m-1, m, m+1 are f[0], f[1], f[2]
+    const int m = r - 1;
+    if (col_out && m >= sc.y0 && m >= 1 && m <= H - 2) {
+      const float d2y = fabsf((f[2][0] - f[1][0]) - (f[1][0] - f[0][0])) + fabsf((f[2][1] - f[1][1]) - (f[1][1] - f[0][1]));
+      sum_y = fmaf(edge_weight(im[1], im[0]), d2y, sum_y);
+    }
+  }
+  sum_x = warp_sum(sum_x);
+  sum_y = warp_sum(sum_y);
+  if (lane == 0) {
+    float* dst = sums + ((size_t)sc.level * P.T.B + sc.b) * 2;
+    atomicAdd(dst, sum_x);
+    atomicAdd(dst + 1, sum_y);
+  }
+}
+
+__global__ void smooth_finalize_kernel(const __grid_constant__ SmoothParams P, const float* __restrict__ sums,
+                                       float* __restrict__ loss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.T.B) return;
+  float acc = 0.0f;
+  for (int l = 0; l < P.T.nlevels; ++l) {
+    const float H = (float)P.lv[l].H, W = (float)P.lv[l].W;
+    const float* s = sums + ((size_t)l * P.T.B + b) * 2;
+    acc += (s[0] / (2.0f * H * (W - 2.0f)) + s[1] / (2.0f * (H - 2.0f) * W)) / 2.0f;   // :165-166
+  }
+  loss[b] = acc;
+}
+
+// --------------------------------------------------------------------------------- smooth bwd
+// gflow[p] = ( sx[p-1] - 2 sx[p] + sx[p+1]  +  sy[p-1] - 2 sy[p] + sy[p+1] ) / 20 with
+// sx[m] = cx * wx[m] * sign(d2x[m]) for 1 <= m <= W-2 (0 elsewhere), sy likewise along rows.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restrict__ g_loss) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Strip sc;
+  if (!locate_strip<2>(P.T, gw, lane, sc)) return;
+  const uof_smooth_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const float* fb = L.flow + (size_t)sc.b * 2 * plane;
+  const float* ib = L.img + (size_t)(sc.b % P.Bimg) * 3 * plane;
+  float* gb = L.gflow + (size_t)sc.b * 2 * plane;
+  const bool col_in = sc.col >= 0 && sc.col < W;
+  const bool col_out = col_in && lane >= 2 && lane <= 29;
+  const float g = __ldg(g_loss + sc.b);
+  const float cx = g * 0.5f / (2.0f * (float)H * ((float)W - 2.0f));
+  const float cy = g * 0.5f / (2.0f * ((float)H - 2.0f) * (float)W);
+
+  float f[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};     // flow/20 rows r-2, r-1, r
+  float im[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};      // image rows r-1, r
+  float sy[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};    // sy rows m-2, m-1, m   (m = r-1)
+  float gxr[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // x-part of the gradient, rows r-2, r-1, r
+
+  for (int r = sc.y0 - 2; r <= sc.y1 + 1; ++r) {
+    const bool inb = col_in && r >= 0 && r < H;
+    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      f[0][k] = f[1][k];
+      f[1][k] = f[2][k];
+      f[2][k] = inb ? __ldg(fb + off + k * plane) / 20.0f : 0.0f;
+      gxr[0][k] = gxr[1][k];
+      gxr[1][k] = gxr[2][k];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      im[0][c] = im[1][c];
+      im[1][c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
+    }
+    // x part for row r
+    float ir[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ir[c] = __shfl_down_sync(kFullMask, im[1][c], 1);
+    const bool mx_ok = inb && sc.col >= 1 && sc.col <= W - 2;
+    const float wx = mx_ok ? cx * edge_weight(ir, im[1]) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float fl = __shfl_up_sync(kFullMask, f[2][k], 1), fr = __shfl_down_sync(kFullMask, f[2][k], 1);
+      const float s = wx * sgn((fr - f[2][k]) - (f[2][k] - fl));
+      gxr[2][k] = __shfl_up_sync(kFullMask, s, 1) - 2.0f * s + __shfl_down_sync(kFullMask, s, 1);
+    }
+    // y part: sy at row m = r-1
+    const int m = r - 1;
+    const bool my_ok = col_in && m >= 1 && m <= H - 2;
+    const float wy = my_ok ? cy * edge_weight(im[1], im[0]) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      sy[0][k] = sy[1][k];
+      sy[1][k] = sy[2][k];
+      sy[2][k] = wy * sgn((f[2][k] - f[1][k]) - (f[1][k] - f[0][k]));
+    }
+    // output row p = r-2: sy rows p-1, p, p+1 are sy[0..2]; x part is gxr[0]
+    const int p = r - 2;
+    if (p >= sc.y0 && p < sc.y1 && col_out) {
+      const size_t o = (size_t)p * W + sc.col;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) gb[o + k * plane] = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) / 20.0f;
+    }
+  }
+}
+
+int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, int B, int Bimg, int halo, bool bwd) {
+  UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "smooth_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
+  UOF_REQUIRE(B > 0 && Bimg > 0 && B % Bimg == 0, "smooth_loss: flow batch %d must be a multiple of image batch %d", B, Bimg);
+  int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
+  for (int l = 0; l < nlevels; ++l) {
+    UOF_REQUIRE(levels[l].flow && levels[l].img && levels[l].H >= 3 && levels[l].W >= 3, "smooth_loss: level %d incomplete (needs H,W >= 3)", l);
+    if (bwd) UOF_REQUIRE(levels[l].gflow, "smooth_loss_bwd: level %d has no gradient buffer", l);
+    P.lv[l] = levels[l];
+    H[l] = levels[l].H;
+    W[l] = levels[l].W;
+  }
+  P.Bimg = Bimg;
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo) > 0, "smooth_loss: problem too large");
+  return UOF_OK;
+}
+
+// ------------------------------------------------------------------------------------- consis
+struct ConsisParams {
+  uof_consis_level lv[UOF_MAX_LEVELS];
+  int warp_begin[UOF_MAX_LEVELS + 1];
+  int warps_per_sample[UOF_MAX_LEVELS];
+  int nlevels, B;
+};
+constexpr int kConsisPxPerWarp = 32 * 8;
+
+__device__ __forceinline__ bool locate_chunk(const ConsisParams& P, int gw, int& level, int& b, int& px0) {
+  if (gw >= P.warp_begin[P.nlevels]) return false;
+  int l = 0;
+  while (l + 1 < P.nlevels && gw >= P.warp_begin[l + 1]) ++l;
+  const int local = gw - P.warp_begin[l];
+  level = l;
+  b = local / P.warps_per_sample[l];
+  px0 = (local % P.warps_per_sample[l]) * kConsisPxPerWarp;
+  return true;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int level, b, px0;
+  if (!locate_chunk(P, gw, level, b, px0)) return;
+  const uof_consis_level& L = P.lv[level];
+  const int plane = L.H * L.W;
+  const float* ff = L.flow_fwd + (size_t)b * 2 * plane;
+  const float* fb = L.flow_bwd + (size_t)b * 2 * plane;
+  const float* wf = L.weight_fwd + (size_t)b * plane;
+  float num = 0.0f, den = 0.0f;
+#pragma unroll
+  for (int it = 0; it < kConsisPxPerWarp / 32; ++it) {
+    const int p = px0 + it * 32 + lane;
+    if (p < plane) {
+      const float ax = __ldg(ff + p), ay = __ldg(ff + plane + p);
+      const float bx = __ldg(fb + p), by = __ldg(fb + plane + p);
+      const float occ = 1.0f - __ldg(wf + p);                                  // :187
+      const float na = sqrtf(ax * ax + ay * ay) + kEps, nb = sqrtf(bx * bx + by * by) + kEps;   // :49
+      num = fmaf(fabsf(ax / na + bx / nb) + fabsf(ay / na + by / nb), occ, num);   // :191
+      den += occ;
+    }
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  if (lane == 0) {
+    float* dst = sums + ((size_t)level * P.B + b) * 2;
+    atomicAdd(dst, num);
+    atomicAdd(dst + 1, den);
+  }
+}
+
+__global__ void consis_finalize_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums,
+                                       float* __restrict__ loss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  float acc = 0.0f;
+  for (int l = 0; l < P.nlevels; ++l) {
+    const float n = (float)P.lv[l].H * (float)P.lv[l].W;
+    const float* s = sums + ((size_t)l * P.B + b) * 2;
+    acc += (s[0] / (2.0f * n)) / (s[1] / n + kEps);   // :189-192
+  }
+  loss[b] = acc;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+consis_bwd_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums, const float* __restrict__ g_loss) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int level, b, px0;
+  if (!locate_chunk(P, gw, level, b, px0)) return;
+  const uof_consis_level& L = P.lv[level];
+  const int plane = L.H * L.W;
+  const float* ff = L.flow_fwd + (size_t)b * 2 * plane;
+  const float* fb = L.flow_bwd + (size_t)b * 2 * plane;
+  const float* wf = L.weight_fwd + (size_t)b * plane;
+  float* gf = L.gflow_fwd + (size_t)b * 2 * plane;
+  const float n = (float)plane;
+  const float coef = __ldg(g_loss + b) / (2.0f * n) / (sums[((size_t)level * P.B + b) * 2 + 1] / n + kEps);
+#pragma unroll
+  for (int it = 0; it < kConsisPxPerWarp / 32; ++it) {
+    const int p = px0 + it * 32 + lane;
+    if (p < plane) {
+      const float ax = __ldg(ff + p), ay = __ldg(ff + plane + p);
+      const float bx = __ldg(fb + p), by = __ldg(fb + plane + p);
+      const float occ = 1.0f - __ldg(wf + p);
+      const float ra = sqrtf(ax * ax + ay * ay), na = ra + kEps, nb = sqrtf(bx * bx + by * by) + kEps;
+      const float ux = sgn(ax / na + bx / nb) * coef * occ, uy = sgn(ay / na + by / nb) * coef * occ;
+      // d(a_i/na)/d a_j = delta_ij/na - a_i a_j/(ra*na^2); torch.norm's subgradient at 0 is 0
+      const float k = ra > 0.0f ? (ux * ax + uy * ay) / (ra * na * na) : 0.0f;
+      gf[p] = ux / na - k * ax;
+      gf[plane + p] = uy / na - k * ay;
+    }
+  }
+}
+
+int fill_consis(ConsisParams& P, const uof_consis_level* levels, int nlevels, int B, bool bwd) {
+  UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "consis_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
+  UOF_REQUIRE(B > 0, "consis_loss: bad batch %d", B);
+  long long total = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    const uof_consis_level& L = levels[l];
+    UOF_REQUIRE(L.flow_fwd && L.flow_bwd && L.weight_fwd && L.H > 0 && L.W > 0, "consis_loss: level %d incomplete", l);
+    if (bwd) UOF_REQUIRE(L.gflow_fwd, "consis_loss_bwd: level %d has no gradient buffer", l);
+    UOF_REQUIRE((long long)L.H * L.W < (1ll << 30), "consis_loss: level %d too large", l);
+    P.lv[l] = L;
+    P.warps_per_sample[l] = ceil_div(L.H * L.W, kConsisPxPerWarp);
+    P.warp_begin[l] = (int)total;
+    total += (long long)P.warps_per_sample[l] * B;
+    UOF_REQUIRE(total < (1ll << 30), "consis_loss: problem too large");
+  }
+  P.warp_begin[nlevels] = (int)total;
+  P.nlevels = nlevels;
+  P.B = B;
+  return UOF_OK;
+}
+
+}  // namespace
+}  // namespace uof
+
+using namespace uof;
+
+extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg, float* sums, float* loss,
+                                   uof_stream_t stream_) {
+  UOF_REQUIRE(sums && loss, "smooth_loss_fwd: null output");
+  SmoothParams P;
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
+  smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  smooth_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
+  count_launch(3);
+  return check_launch("smooth_loss_fwd");
+}
+
+extern "C" int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg, const float* g_loss,
+                                   uof_stream_t stream_) {
+  UOF_REQUIRE(g_loss, "smooth_loss_bwd: null input");
+  SmoothParams P;
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 2, true)) return rc;
+  smooth_bwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                      static_cast<cudaStream_t>(stream_)>>>(P, g_loss);
+  count_launch();
+  return check_launch("smooth_loss_bwd");
+}
+
+extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, int B, float* sums, float* loss,
+                                   uof_stream_t stream_) {
+  UOF_REQUIRE(sums && loss, "consis_loss_fwd: null output");
+  ConsisParams P;
+  if (int rc = fill_consis(P, levels, nlevels, B, false)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
+  consis_fwd_kernel<<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  consis_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
+  count_launch(3);
+  return check_launch("consis_loss_fwd");
+}
+
+extern "C" int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, const float* sums,
+                                   const float* g_loss, uof_stream_t stream_) {
+  UOF_REQUIRE(sums && g_loss, "consis_loss_bwd: null input");
+  ConsisParams P;
+  if (int rc = fill_consis(P, levels, nlevels, B, true)) return rc;
+  consis_bwd_kernel<<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                      static_cast<cudaStream_t>(stream_)>>>(P, sums, g_loss);
+  count_launch();
+  return check_launch("consis_loss_bwd");
+}

@@ -1,0 +1,355 @@
+// a4+a5+a6 fused: photometric weight maps, masked L1 and masked SSIM losses, both directions,
+// every pyramid level in ONE launch (forward) / ONE launch (backward).
+// Replaces, in /root/reference/core/networks/model_flow_paper.py, compute_diff_weight (:101-134),
+// compute_loss_with_mask x2 (:90-99), compute_loss_ssim x2 (:137-148) and
+// pytorch_ssim/ssim.py:4-19 -- ~350 ATen launches and ~40 full-size temporaries forward.
+//
+// Design ("marching warp"): a warp owns a strip of 32 image columns (30 or 28 of them outputs, the
+// rest halo) and marches down R rows.  Each lane loads its pixel's 9 values (I, W_l, W_r) straight
+// from global memory (128 B coalesced per plane per row), computes the weights in registers, gets its
+// left/right neighbours with warp shuffles (horizontal 3-tap sums) and keeps a 3-row register ring
+// for the vertical 3-tap sums.  No shared memory, no temporaries in HBM; per-sample reductions are
+// warp-shuffle trees + one fp32 atomic per warp and quantity.  The backward pass chains two such
+// box filters (5x5 footprint) with a second ring.
+#include "strips.cuh"
+
+namespace uof {
+namespace {
+
+constexpr float C1 = 0.01f * 0.01f;      // ssim.py:5
+constexpr float C2 = 0.03f * 0.03f;      // ssim.py:6
+constexpr float kEps = 1e-12f;           // model_flow_paper.py:97,145
+constexpr float kInv9 = 1.0f / 9.0f;
+constexpr int kWarpsPerBlock = 4;
+
+struct PhotoParams {
+  uof_photo_level lv[UOF_MAX_LEVELS];
+  StripTable T;
+};
+
+struct PixelWeights {
+  float dl, dr, wl, wr;
+};
+
+// model_flow_paper.py:111-129 for one pixel.
+__device__ __forceinline__ PixelWeights pixel_weights(const float* I, const float* L, const float* R) {
+  PixelWeights o;
+  o.dl = (fabsf(I[0] - L[0]) + fabsf(I[1] - L[1]) + fabsf(I[2] - L[2])) / 3.0f;
+  o.dr = (fabsf(I[0] - R[0]) + fabsf(I[1] - R[1]) + fabsf(I[2] - R[2])) / 3.0f;
+  const float vl = (L[0] == 0.0f && L[1] == 0.0f && L[2] == 0.0f) ? 0.0f : 1.0f;
+  const float vr = (R[0] == 0.0f && R[1] == 0.0f && R[2] == 0.0f) ? 0.0f : 1.0f;
+  const float mx = fmaxf(o.dl, o.dr);
+  const float el = expf(o.dl - mx), er = expf(o.dr - mx);
+  const float inv = 1.0f / (el + er);
+  const float al = 1.0f - el * inv - 0.5f, ar = 1.0f - er * inv - 0.5f;
+  o.wl = 2.0f * expf(-(al * al) / 0.03f) * vl;
+  o.wr = 2.0f * expf(-(ar * ar) / 0.03f) * vr;
+  return o;
+}
+
+__device__ __forceinline__ void load_pixel(const uof_photo_level& L, size_t base, size_t plane, bool inb, float* I,
+                                           float* Wl, float* Wr) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    I[c] = inb ? __ldg(L.img + base + c * plane) : 0.0f;
+    Wl[c] = inb ? __ldg(L.warped_l + base + c * plane) : 0.0f;
+    Wr[c] = inb ? __ldg(L.warped_r + base + c * plane) : 0.0f;
+  }
+}
+
+// horizontal 3-tap sums of (x, y, x^2, y^2, xy) across adjacent lanes
+__device__ __forceinline__ void hsum_moments(float xv, float yv, float* m) {
+  const float xl = __shfl_up_sync(kFullMask, xv, 1), xr = __shfl_down_sync(kFullMask, xv, 1);
+  const float yl = __shfl_up_sync(kFullMask, yv, 1), yr = __shfl_down_sync(kFullMask, yv, 1);
+  m[0] = xl + xv + xr;
+  m[1] = yl + yv + yr;
+  m[2] = fmaf(xr, xr, fmaf(xv, xv, xl * xl));
+  m[3] = fmaf(yr, yr, fmaf(yv, yv, yl * yl));
+  m[4] = fmaf(xr, yr, fmaf(xv, yv, xl * yl));
+}
+
+struct SsimTerms {
+  float mux, muy, A1, A2, B1, B2, S;
+};
+
+__device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float* s1, const float* s2) {
+  SsimTerms t;
+  t.mux = (s0[0] + s1[0] + s2[0]) * kInv9;
+  t.muy = (s0[1] + s1[1] + s2[1]) * kInv9;
+  const float sxx = (s0[2] + s1[2] + s2[2]) * kInv9;
+  const float syy = (s0[3] + s1[3] + s2[3]) * kInv9;
+  const float sxy = (s0[4] + s1[4] + s2[4]) * kInv9;
+  const float sig_x = sxx - t.mux * t.mux, sig_y = syy - t.muy * t.muy, sig_xy = sxy - t.mux * t.muy;
+  t.A1 = 2.0f * t.mux * t.muy + C1;
+  t.A2 = 2.0f * sig_xy + C2;
+  t.B1 = t.mux * t.mux + t.muy * t.muy + C1;
+  t.B2 = sig_x + sig_y + C2;
+  t.S = (t.A1 * t.A2) / (t.B1 * t.B2);
+  return t;
+}
+
+// -------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Strip sc;
+  if (!locate_strip<1>(P.T, gw, lane, sc)) return;
+  const uof_photo_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const size_t img_base = (size_t)sc.b * 3 * plane, map_base = (size_t)sc.b * plane;
+  const bool col_in = sc.col >= 0 && sc.col < W;
+  const bool col_out = col_in && lane >= 1 && lane <= 30;
+
+  float ring[3][2][3][5];   // [row][direction][channel][moment]
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) ring[a][d][c][k] = 0.0f;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  for (int r = sc.y0 - 1; r <= sc.y1; ++r) {
+    const bool inb = col_in && r >= 0 && r < H;
+    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
+    float I[3], Wl[3], Wr[3];
+    load_pixel(L, img_base + off, plane, inb, I, Wl, Wr);
+    PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
+    if (inb) pw = pixel_weights(I, Wl, Wr);
+    if (inb && col_out && r >= sc.y0 && r < sc.y1) {
+      acc[0] = fmaf(pw.dl, pw.wl, acc[0]);
+      acc[1] += pw.wl;
+      acc[2] = fmaf(pw.dr, pw.wr, acc[2]);
+      acc[3] += pw.wr;
+      if (L.weight_l) L.weight_l[map_base + off] = pw.wl;
+      if (L.weight_r) L.weight_r[map_base + off] = pw.wr;
+      if (L.diff_l) L.diff_l[map_base + off] = pw.dl;
+      if (L.diff_r) L.diff_r[map_base + off] = pw.dr;
+    }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const float wd = d ? pw.wr : pw.wl;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          ring[0][d][c][k] = ring[1][d][c][k];
+          ring[1][d][c][k] = ring[2][d][c][k];
+        }
+        hsum_moments(I[c] * wd, (d ? Wr[c] : Wl[c]) * wd, ring[2][d][c]);
+      }
+    }
+    const int q = r - 1;   // row whose 3x3 window is now complete
+    if (q >= sc.y0 && col_out) {
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const SsimTerms t = ssim_from_sums(ring[0][d][c], ring[1][d][c], ring[2][d][c]);
+          acc[4 + d] += fminf(fmaxf((1.0f - t.S) * 0.5f, 0.0f), 1.0f);   // model_flow_paper.py:144
+        }
+    }
+  }
+  float* dst = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) atomicAdd(dst + k, v);
+  }
+}
+
+// loss_pixel[b] = sum_l sum_d mean(d*w)/(mean(w)+eps);  loss_ssim[b] likewise (model_flow_paper.py:94-98,141-147)
+__global__ void photo_loss_finalize_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
+                                           float* __restrict__ loss_pixel, float* __restrict__ loss_ssim) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.T.B) return;
+  float lp = 0.0f, ls = 0.0f;
+  for (int l = 0; l < P.T.nlevels; ++l) {
+    const float n = (float)P.lv[l].H * (float)P.lv[l].W;
+    const float* s = sums + ((size_t)l * P.T.B + b) * 6;
+    // reference order: forward/right term first, then backward/left (:241-245)
+    lp += (s[2] / n) / (s[3] / n + kEps) + (s[0] / n) / (s[1] / n + kEps);
+    ls += (s[5] / (3.0f * n)) / (s[3] / n + kEps) + (s[4] / (3.0f * n)) / (s[1] / n + kEps);
+  }
+  loss_pixel[b] = lp;
+  loss_ssim[b] = ls;
+}
+
+// ------------------------------------------------------------------------------------- backward
+// blockIdx.y = direction (0: left/"bwd", 1: right/"fwd").  Output: d loss / d warped_{l,r}.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
+                      const float* __restrict__ g_pixel, const float* __restrict__ g_ssim) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int dir = blockIdx.y;
+  Strip sc;
+  if (!locate_strip<2>(P.T, gw, lane, sc)) return;
+  const uof_photo_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const size_t img_base = (size_t)sc.b * 3 * plane;
+  const bool col_in = sc.col >= 0 && sc.col < W;
+  const bool col_out = col_in && lane >= 2 && lane <= 29;
+  float* gout = dir ? L.gwarped_r : L.gwarped_l;
+
+  const float n = (float)H * (float)W;
+  const float* s = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
+  const float inv_div = 1.0f / (s[dir ? 3 : 1] / n + kEps);
+  const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;        // d loss / d |I_c - W_c| per unit weight
+  const float coef_ss = -0.5f * __ldg(g_ssim + sc.b) * inv_div / (3.0f * n);  // d loss / d S where the clamp passes
+
+  float mom[3][3][5];    // [row][channel][moment]        rows r-2, r-1, r
+  float abc[3][3][3];    // [row][channel][a,b,c] h-sums  rows q-2, q-1, q   (q = r-1)
+  float xy[3][3][2];     // [row][channel][x,y]           rows r-2, r-1, r
+  float wl1[3][4];       // [row][w, l1grad_c0..2]        rows r-2, r-1, r
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) mom[a][c][k] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) abc[a][c][k] = 0.0f;
+      xy[a][c][0] = xy[a][c][1] = 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wl1[a][k] = 0.0f;
+  }
+
+  for (int r = sc.y0 - 2; r <= sc.y1 + 1; ++r) {
+    const bool inb = col_in && r >= 0 && r < H;
+    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
+    float I[3], Wl[3], Wr[3];
+    load_pixel(L, img_base + off, plane, inb, I, Wl, Wr);
+    PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
+    if (inb) pw = pixel_weights(I, Wl, Wr);
+    const float wd = dir ? pw.wr : pw.wl;
+
+    // shift the per-row rings and push row r
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        mom[0][c][k] = mom[1][c][k];
+        mom[1][c][k] = mom[2][c][k];
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        xy[0][c][k] = xy[1][c][k];
+        xy[1][c][k] = xy[2][c][k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      wl1[0][k] = wl1[1][k];
+      wl1[1][k] = wl1[2][k];
+    }
+    wl1[2][0] = wd;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float wc = dir ? Wr[c] : Wl[c];
+      const float df = I[c] - wc;
+      const float sg = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
+      wl1[2][1 + c] = -sg * coef_l1 * wd;          // d(masked L1)/d W_c
+      xy[2][c][0] = I[c] * wd;
+      xy[2][c][1] = wc * wd;
+      hsum_moments(xy[2][c][0], xy[2][c][1], mom[2][c]);
+    }
+
+    // row q = r-1: SSIM derivative coefficients w.r.t. the pooled (mu_y, E[y^2], E[xy]) at (q, col)
+    const int q = r - 1;
+    if (q >= sc.y0 - 1) {
+      const bool q_in = col_in && q >= 0 && q < H;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float a = 0.0f, bb = 0.0f, cc = 0.0f;
+        if (q_in) {
+          const SsimTerms t = ssim_from_sums(mom[0][c], mom[1][c], mom[2][c]);
+          const float term = (1.0f - t.S) * 0.5f;
+          if (term >= 0.0f && term <= 1.0f) {        // clamp passes gradient on the closed interval
+            const float D = t.B1 * t.B2;
+            const float dN = 2.0f * t.mux * (t.A2 - t.A1);
+            const float dD = 2.0f * t.muy * (t.B2 - t.B1);
+            a = coef_ss * (dN - t.S * dD) / D;
+            bb = coef_ss * (-t.S / t.B2);
+            cc = coef_ss * (2.0f * t.A1 / D);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          abc[0][c][k] = abc[1][c][k];
+          abc[1][c][k] = abc[2][c][k];
+        }
+        abc[2][c][0] = __shfl_up_sync(kFullMask, a, 1) + a + __shfl_down_sync(kFullMask, a, 1);
+        abc[2][c][1] = __shfl_up_sync(kFullMask, bb, 1) + bb + __shfl_down_sync(kFullMask, bb, 1);
+        abc[2][c][2] = __shfl_up_sync(kFullMask, cc, 1) + cc + __shfl_down_sync(kFullMask, cc, 1);
+      }
+    }
+
+    // row p = r-2: all nine coefficient neighbours are in the ring
+    const int p = r - 2;
+    if (p >= sc.y0 && p < sc.y1 && col_out) {
+      const size_t o = img_base + (size_t)p * W + sc.col;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float A = abc[0][c][0] + abc[1][c][0] + abc[2][c][0];
+        const float Bq = abc[0][c][1] + abc[1][c][1] + abc[2][c][1];
+        const float Cq = abc[0][c][2] + abc[1][c][2] + abc[2][c][2];
+        const float gy = (A + 2.0f * xy[0][c][1] * Bq + xy[0][c][0] * Cq) * kInv9;
+        gout[o + c * plane] = fmaf(gy, wl1[0][0], wl1[0][1 + c]);
+      }
+    }
+  }
+}
+
+int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd) {
+  UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "photo_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
+  UOF_REQUIRE(B > 0, "photo_loss: bad batch %d", B);
+  int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
+  for (int l = 0; l < nlevels; ++l) {
+    const uof_photo_level& L = levels[l];
+    UOF_REQUIRE(L.img && L.warped_l && L.warped_r && L.H > 0 && L.W > 0, "photo_loss: level %d incomplete", l);
+    if (bwd) UOF_REQUIRE(L.gwarped_l && L.gwarped_r, "photo_loss_bwd: level %d has no gradient buffers", l);
+    P.lv[l] = L;
+    H[l] = L.H;
+    W[l] = L.W;
+  }
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo) > 0, "photo_loss: problem too large");
+  return UOF_OK;
+}
+
+}  // namespace
+}  // namespace uof
+
+using namespace uof;
+
+extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B, float* sums, float* loss_pixel,
+                                  float* loss_ssim, uof_stream_t stream_) {
+  UOF_REQUIRE(sums && loss_pixel && loss_ssim, "photo_loss_fwd: null output");
+  PhotoParams P;
+  if (int rc = fill_params(P, levels, nlevels, B, 1, false)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 6 * sizeof(float), stream));
+  const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
+  photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
+  count_launch(3);
+  return check_launch("photo_loss_fwd");
+}
+
+extern "C" int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, int B, const float* sums,
+                                  const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream_) {
+  UOF_REQUIRE(sums && g_loss_pixel && g_loss_ssim, "photo_loss_bwd: null input");
+  PhotoParams P;
+  if (int rc = fill_params(P, levels, nlevels, B, 2, true)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid(ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), 2);
+  photo_loss_bwd_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(P, sums, g_loss_pixel, g_loss_ssim);
+  count_launch();
+  return check_launch("photo_loss_bwd");
+}

@@ -1,0 +1,120 @@
+"""`Model_flow` with the reference's interface (model_flow_paper.py:14-255) on the CUDA hot path.
+
+`forward(inputs) -> {'loss_pixel','loss_ssim','loss_flow_smooth','loss_flow_consis'}` each `(B,)`,
+`inference_flow(img1, img2) -> (B,2,H,W)`, the `compute_*` / pyramid helper methods, and the same
+98 state-dict keys.  What changes is how the step is executed:
+
+* the three encoder passes run as one 3B batch and the two decoder passes as one 2B batch
+  ([centre;centre] vs [left;right]) -- the per-sample math is unchanged;
+* cost volume, warps, image pyramid and every loss run as hand-written sm_100a kernels
+  (`unopticalflow_b200.ops`), with all pyramid levels and both directions of a loss in one launch;
+* scale 3 is not warped in `forward` because no loss reads it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .structures import FeaturePyramid, PWC_tf
+
+
+class Model_flow(nn.Module):
+    def __init__(self, cfg, align_corners=None):
+        super().__init__()
+        self.align_corners = ops.DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+        self.fpyramid = FeaturePyramid()
+        self.pwc_model = PWC_tf(align_corners=self.align_corners)
+        if cfg.mode == 'depth' or cfg.mode == 'flowposenet':        # model_flow_paper.py:19-24
+            for p in self.parameters():
+                p.requires_grad = False
+        self.dataset = cfg.dataset
+        self.num_scales = cfg.num_scales
+        self.flow_consist_alpha = cfg.h_flow_consist_alpha
+        self.flow_consist_beta = cfg.h_flow_consist_beta
+
+    # ---- reference helper API (list-of-tensors in, (B,) out) ------------------------------------
+    def get_flow_norm(self, flow, p=2):
+        return torch.norm(flow, p=p, dim=1).unsqueeze(1) + 1e-12
+
+    def get_flow_normalization(self, flow, p=2):
+        return flow / self.get_flow_norm(flow, p).repeat(1, 2, 1, 1)
+
+    def generate_img_pyramid(self, img, num_pyramid):
+        return ops.img_pyramid(img, num_pyramid)
+
+    def warp_flow_pyramid(self, img_pyramid, flow_pyramid):
+        return [ops.warp_flow(i, f, use_mask=True, align_corners=self.align_corners)
+                for i, f in zip(img_pyramid, flow_pyramid)]
+
+    def compute_diff_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
+        """-> diff_bwd, diff_fwd, weight_bwd, weight_fwd (model_flow_paper.py:101-134).  Weights come from
+        the fused kernel (detached, as in the reference); the differentiable diff maps are plain tensor ops."""
+        S = self.num_scales
+        _, _, w_b, w_f = ops.photometric_losses([t.detach() for t in img_pyramid[:S]],
+                                                [t.detach() for t in img_pyramid_from_l[:S]],
+                                                [t.detach() for t in img_pyramid_from_r[:S]], S)
+        d_b = [(img_pyramid[s] - img_pyramid_from_l[s]).abs().mean(1, True) for s in range(S)]
+        d_f = [(img_pyramid[s] - img_pyramid_from_r[s]).abs().mean(1, True) for s in range(S)]
+        return d_b, d_f, w_b, w_f
+
+    def compute_loss_with_mask(self, diff_list, occ_mask_list):
+        total = 0
+        for s in range(self.num_scales):
+            d, m = diff_list[s], occ_mask_list[s]
+            total = total + (d * m).mean((1, 2, 3)) / (m.mean((1, 2, 3)) + 1e-12)
+        return total
+
+    def compute_loss_ssim(self, img_pyramid, img_warped_pyramid, occ_mask_list):
+        total = 0
+        for s in range(self.num_scales):
+            img, wp, m = img_pyramid[s], img_warped_pyramid[s], occ_mask_list[s]
+            s_map = ops.SSIM(img * m, wp * m)
+            total = total + torch.clamp((1.0 - s_map) / 2.0, 0, 1).mean((1, 2, 3)) / (m.mean((1, 2, 3)) + 1e-12)
+        return total
+
+    def compute_loss_flow_smooth(self, optical_flows, img_pyramid):
+        return ops.flow_smooth_loss(optical_flows, img_pyramid, self.num_scales)
+
+    def compute_loss_flow_consis(self, fwd_flow_pyramid, bwd_flow_pyramid, occ_mask_list):
+        return ops.flow_consis_loss(fwd_flow_pyramid, bwd_flow_pyramid, occ_mask_list, self.num_scales)
+
+    # ---- north-star extras (absent from the reference) -----------------------------
+    def get_occlusion_mask_from_flow(self, flow):
+        """(B,2,H,W) flow -> (B,1,H,W) soft visibility clamp(range_map, 0, 1)."""
+        return ops.occlusion_mask(flow.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+    def get_consistent_mask(self, flow_fwd, flow_rev):
+        return ops.fb_consistency_mask(flow_fwd, flow_rev, self.flow_consist_alpha, self.flow_consist_beta,
+                                       self.align_corners)
+
+    # ---- inference -----------------------------------------------------------------------------------
+    def inference_flow(self, img1, img2):
+        B = img1.shape[0]
+        feats = self.fpyramid(torch.cat((img1, img2), 0))
+        return self.pwc_model([f[:B] for f in feats], [f[B:] for f in feats], [img1.shape[2], img1.shape[3]])[0]
+
+    # ---- training step ----------------------------------------------------------------------------------
+    def forward(self, inputs, output_flow=False):
+        assert inputs.shape[1] == 3
+        B, H, W = inputs.shape[0], int(inputs.shape[2] / 3), inputs.shape[3]
+        S = self.num_scales
+        imgl, img, imgr = inputs[:, :, :H], inputs[:, :, H:2 * H], inputs[:, :, 2 * H:3 * H]
+
+        feats = self.fpyramid(torch.cat((imgl, img, imgr), 0))                      # one 3B encoder pass
+        f1 = [torch.cat((f[B:2 * B], f[B:2 * B]), 0) for f in feats]                 # [centre ; centre]
+        f2 = [torch.cat((f[:B], f[2 * B:]), 0) for f in feats]                       # [left   ; right ]
+        flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
+
+        pyr_l, pyr_c, pyr_r = ops.img_pyramid(imgl, S), ops.img_pyramid(img, S), ops.img_pyramid(imgr, S)
+        warped = [ops.warp_flow(torch.cat((pyr_l[s], pyr_r[s]), 0), flows[s], use_mask=True,
+                                align_corners=self.align_corners) for s in range(S)]  # [from_l ; from_r]
+
+        loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
+        smooth = ops.flow_smooth_loss(flows, pyr_c, S)                               # (2B,): [bwd ; fwd]
+        consis = ops.flow_consis_loss([f[B:] for f in flows[:S]], [f[:B] for f in flows[:S]], w_fwd, S)
+        loss_pack = {'loss_pixel': loss_pixel, 'loss_ssim': loss_ssim,
+                     'loss_flow_smooth': smooth[B:] + smooth[:B], 'loss_flow_consis': consis}
+        if output_flow:
+            return loss_pack, [f[B:] for f in flows], [f[:B] for f in flows]
+        return loss_pack

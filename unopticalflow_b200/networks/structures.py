@@ -1,0 +1,105 @@
+"""Encoder / decoder skeleton around the CUDA operators.
+
+Mirrors the reference's `core/networks/structures` API: `conv`, `FeaturePyramid`
+(feature_pyramid.py:7-36), `PWC_tf` (pwc_tf.py:16-179) with its `corr` / `warp` seams, and
+`warp_flow`.  By the north star the convolutions stay in PyTorch/cuDNN; `corr` and `warp` run the
+hand-written sm_100a kernels.  State-dict keys equal the reference's 98 keys, so reference
+checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops import warp_flow  # noqa: F401  (re-exported like structures/__init__.py:5)
+
+_ENCODER = (16, 32, 64, 96, 128, 196)
+_DENSE = (128, 128, 96, 64, 32)
+_LEVEL_C = {6: 196, 5: 128, 4: 96, 3: 64, 2: 32}
+_CONTEXT = ((128, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1))
+
+
+def conv(in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1):
+    """Conv2d + LeakyReLU(0.1) (net_utils.py:7-11)."""
+    return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=padding,
+                                   dilation=dilation, bias=True), nn.LeakyReLU(0.1))
+
+
+class FeaturePyramid(nn.Module):
+    def __init__(self):
+        super().__init__()
+        cin = 3
+        for k, cout in enumerate(_ENCODER):
+            setattr(self, 'conv%d' % (2 * k + 1), conv(cin, cout, stride=2))
+            setattr(self, 'conv%d' % (2 * k + 2), conv(cout, cout, stride=1))
+            cin = cout
+
+    def forward(self, img):
+        feats, t = [], img
+        for k in range(len(_ENCODER)):
+            t = getattr(self, 'conv%d' % (2 * k + 2))(getattr(self, 'conv%d' % (2 * k + 1))(t))
+            feats.append(t)
+        return tuple(feats)
+
+
+class PWC_tf(nn.Module):
+    def __init__(self, md=4, align_corners=None):
+        super().__init__()
+        if md != 4:
+            raise ValueError('the cost-volume kernel is built for md=4 (81 displacements)')
+        self.align_corners = align_corners
+        self.corr = self.corr_cuda          # seam, like `self.corr = self.corr_naive` (pwc_tf.py:19)
+        nd = (2 * md + 1) ** 2
+        w = _DENSE
+        for lvl in (6, 5, 4, 3, 2):
+            cin = nd if lvl == 6 else nd + _LEVEL_C[lvl] + 2
+            ins = (cin, w[0], w[0] + w[1], w[1] + w[2], w[2] + w[3])
+            for i in range(5):
+                setattr(self, 'conv%d_%d' % (lvl, i), conv(ins[i], w[i]))
+            setattr(self, 'predict_flow%d' % lvl, self.predict_flow(w[3] + w[4]))
+        cin = w[4] + 2
+        for i, (cout, dil) in enumerate(_CONTEXT):
+            setattr(self, 'dc_conv%d' % (i + 1), conv(cin, cout, padding=dil, dilation=dil))
+            cin = cout
+        self.dc_conv7 = self.predict_flow(cin)
+
+    def predict_flow(self, in_planes):
+        return nn.Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1, bias=True)
+
+    def corr_cuda(self, input1, input2):
+        return ops.corr(input1, input2)
+
+    corr_naive = corr_cuda                  # reference name (pwc_tf.py:97)
+
+    def warp(self, x, flow):
+        return ops.warp_flow(x, flow, use_mask=False, align_corners=self.align_corners)
+
+    def _level(self, lvl, x):
+        x0 = getattr(self, 'conv%d_0' % lvl)(x)
+        x1 = getattr(self, 'conv%d_1' % lvl)(x0)
+        x2 = getattr(self, 'conv%d_2' % lvl)(torch.cat((x0, x1), 1))
+        x3 = getattr(self, 'conv%d_3' % lvl)(torch.cat((x1, x2), 1))
+        x4 = getattr(self, 'conv%d_4' % lvl)(torch.cat((x2, x3), 1))
+        return getattr(self, 'predict_flow%d' % lvl)(torch.cat((x3, x4), 1)), x4
+
+    def forward(self, feature_list_1, feature_list_2, img_hw):
+        flows, up, x4 = {}, None, None
+        for lvl in (6, 5, 4, 3, 2):
+            c1, c2 = feature_list_1[lvl - 1], feature_list_2[lvl - 1]
+            if up is None:
+                flow, x4 = self._level(lvl, self.corr(c1, c2))
+            else:
+                cv = self.corr(c1, self.warp(c2, up))
+                res, x4 = self._level(lvl, torch.cat((cv, c1, up), 1))
+                flow = res + up
+            flows[lvl] = flow
+            if lvl > 2:
+                up = F.interpolate(flow, scale_factor=2.0, mode='bilinear') * 2.0
+        t = torch.cat((flows[2], x4), 1)
+        for i in range(1, 7):
+            t = getattr(self, 'dc_conv%d' % i)(t)
+        flows[2] = flows[2] + self.dc_conv7(t)
+        img_h, img_w = img_hw[0], img_hw[1]
+        return [F.interpolate(flows[2 + s] * 4.0, [img_h // 2 ** s, img_w // 2 ** s], mode='bilinear') for s in range(4)]

@@ -1,0 +1,438 @@
+"""Host-side operators: the reference's operator API backed by libuof_b200.so.
+
+Names, argument meaning and error behaviour mirror the reference seams:
+`corr(f1, f2)` == PWC_tf.corr_naive (pwc_tf.py:97-106), `warp_flow(x, flow, use_mask)` ==
+net_utils.warp_flow (net_utils.py:16-54), `SSIM(x, y)` == pytorch_ssim.SSIM (ssim.py:4-19); the
+loss functions take the same lists-of-tensors as Model_flow.compute_* (model_flow_paper.py:90-195).
+Every op is a `torch.autograd.Function` whose forward/backward enqueue hand-written sm_100a kernels
+on the current CUDA stream.  CPU tensors raise: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConsisLevel, PhotoLevel, SmoothLevel
+
+# grid_sample convention of "the reference executed under the installed torch" (SURVEY F4).
+DEFAULT_ALIGN_CORNERS = False
+NUM_DISPLACEMENTS = 81
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('unopticalflow_b200 operators need CUDA tensors (got device %s); '
+                               'there is no CPU fallback' % t.device)
+        if t.dtype != torch.float32:
+            raise TypeError('unopticalflow_b200 operators are fp32 only (got %s)' % t.dtype)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+# ------------------------------------------------------------------------------------------ a1
+class _CostVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2):
+        f1c, f2c = f1.contiguous(), f2.contiguous()
+        B, C, H, W = f1c.shape
+        out = torch.empty((B, NUM_DISPLACEMENTS, H, W), device=f1.device, dtype=torch.float32)
+        with torch.cuda.device_of(f1c):
+            _lib.call('uof_cost_volume_fwd', _p(f1c), _p(f2c), _p(out), B, C, H, W, NUM_DISPLACEMENTS * H * W, _stream(f1c))
+        ctx.save_for_backward(f1c, f2c)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        f1c, f2c = ctx.saved_tensors
+        B, C, H, W = f1c.shape
+        gout = gout.contiguous()
+        g1, g2 = torch.empty_like(f1c), torch.empty_like(f2c)
+        with torch.cuda.device_of(f1c):
+            _lib.call('uof_cost_volume_bwd', _p(gout), NUM_DISPLACEMENTS * H * W, _p(f1c), _p(f2c), _p(g1), _p(g2),
+                      B, C, H, W, _stream(f1c))
+        return g1, g2
+
+
+def corr(input1: torch.Tensor, input2: torch.Tensor) -> torch.Tensor:
+    """81-displacement cost volume, channel mean.  Drop-in for `PWC_tf.corr` (pwc_tf.py:19,97-106)."""
+    assert input1.shape == input2.shape                       # pwc_tf.py:99
+    _require_cuda(input1, input2)
+    return _CostVolume.apply(input1, input2)
+
+
+# --------------------------------------------------------------------------------------- a2/a3
+def _is_channels_last(x):
+    return (x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] > 1 and not x.is_contiguous()
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+class _WarpFlow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow, use_mask, align_corners):
+        cl = _is_channels_last(x)
+        xc = x if cl else x.contiguous()
+        fc = flow.contiguous()
+        B, C, H, W = xc.shape
+        out = torch.empty_like(xc)     # preserves the memory format
+        with torch.cuda.device_of(xc):
+            _lib.call('uof_warp_fwd', _p(xc), _p(fc), _p(out), B, C, H, W, int(use_mask), int(align_corners), int(cl),
+                      _stream(xc))
+        ctx.save_for_backward(xc, fc)
+        ctx.flags = (int(use_mask), int(align_corners), int(cl))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xc, fc = ctx.saved_tensors
+        use_mask, align_corners, cl = ctx.flags
+        B, C, H, W = xc.shape
+        gout = gout.contiguous(memory_format=torch.channels_last) if cl else gout.contiguous()
+        gx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        gflow = torch.empty_like(fc)
+        with torch.cuda.device_of(xc):
+            _lib.call('uof_warp_bwd', _p(gout), _p(xc), _p(fc), _p(gx), _p(gflow), B, C, H, W, use_mask, align_corners,
+                      cl, _stream(xc))
+        return gx, gflow, None, None
+
+
+def warp_flow(x: torch.Tensor, flow: torch.Tensor, use_mask: bool = False, align_corners: bool | None = None):
+    """Bilinear backward warp (+ validity mask).  Drop-in for `warp_flow` (net_utils.py:16-54)."""
+    B, C, H, W = x.size()
+    if tuple(flow.shape) != (B, 2, H, W):                     # net_utils.py:35-36
+        raise ValueError('the shape of grid {0} is not equal to the shape of flow {1}.'.format(
+            torch.Size((B, 2, H, W)), flow.shape))
+    _require_cuda(x, flow)
+    ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+    return _WarpFlow.apply(x, flow, bool(use_mask), ac)
+
+
+# ------------------------------------------------------------------------------------------ a6
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        xc, yc = x.contiguous(), y.contiguous()
+        B, C, H, W = xc.shape
+        out = torch.empty_like(xc)
+        with torch.cuda.device_of(xc):
+            _lib.call('uof_ssim_fwd', _p(xc), _p(yc), _p(out), B * C, H, W, _stream(xc))
+        ctx.save_for_backward(xc, yc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xc, yc = ctx.saved_tensors
+        B, C, H, W = xc.shape
+        gx, gy = torch.empty_like(xc), torch.empty_like(yc)
+        with torch.cuda.device_of(xc):
+            _lib.call('uof_ssim_bwd', _p(gout.contiguous()), _p(xc), _p(yc), _p(gx), _p(gy), B * C, H, W, _stream(xc))
+        return gx, gy
+
+
+def SSIM(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """SSIM map.  Drop-in for `pytorch_ssim.SSIM` (ssim.py:4-19)."""
+    assert x.shape == y.shape and x.dim() == 4
+    _require_cuda(x, y)
+    return _SSIM.apply(x, y)
+
+
+# ------------------------------------------------------------------------------------ a4+a5+a6
+def _levels(cls, n):
+    return (cls * n)()
+
+
+class _PhotoLoss(torch.autograd.Function):
+    """Fused compute_diff_weight + 2x compute_loss_with_mask + 2x compute_loss_ssim.
+
+    tensors = imgs[S] + warped_l[S] + warped_r[S], or with `stacked` imgs[S] + warped_lr[S] where
+    warped_lr[s] is (2B,3,H,W) = [from-left ; from-right] (what the 2B-batched decoder produces), in
+    which case the gradient comes back as one (2B,3,H,W) tensor per level."""
+
+    @staticmethod
+    def forward(ctx, S, want_diff, stacked, *tensors):
+        imgs = [t.contiguous() for t in tensors[:S]]
+        B = imgs[0].shape[0]
+        if stacked:
+            both = [t.contiguous() for t in tensors[S:2 * S]]
+            wl, wr = [t[:B] for t in both], [t[B:] for t in both]
+        else:
+            both = []
+            wl = [t.contiguous() for t in tensors[S:2 * S]]
+            wr = [t.contiguous() for t in tensors[2 * S:3 * S]]
+        dev = imgs[0].device
+        lv = _levels(PhotoLevel, S)
+        weights_l, weights_r, diffs_l, diffs_r = [], [], [], []
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            assert wl[s].shape == imgs[s].shape and wr[s].shape == imgs[s].shape and imgs[s].shape[1] == 3
+            weights_l.append(torch.empty((B, 1, H, W), device=dev))
+            weights_r.append(torch.empty((B, 1, H, W), device=dev))
+            if want_diff:
+                diffs_l.append(torch.empty((B, 1, H, W), device=dev))
+                diffs_r.append(torch.empty((B, 1, H, W), device=dev))
+            lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(),
+                               weights_l[s].data_ptr(), weights_r[s].data_ptr(),
+                               diffs_l[s].data_ptr() if want_diff else None, diffs_r[s].data_ptr() if want_diff else None,
+                               None, None, H, W)
+        sums = torch.empty((S, B, 6), device=dev)
+        loss_pixel, loss_ssim = torch.empty(B, device=dev), torch.empty(B, device=dev)
+        with torch.cuda.device_of(imgs[0]):
+            _lib.call('uof_photo_loss_fwd', lv, S, B, _p(sums), _p(loss_pixel), _p(loss_ssim), _stream(imgs[0]))
+        if stacked:
+            ctx.save_for_backward(sums, *imgs, *both)
+        else:
+            ctx.save_for_backward(sums, *imgs, *wl, *wr)
+        ctx.S, ctx.stacked = S, stacked
+        outs = (loss_pixel, loss_ssim, *weights_l, *weights_r, *diffs_l, *diffs_r)
+        ctx.mark_non_differentiable(*outs[2:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pixel, g_ssim, *unused):
+        S, stacked = ctx.S, ctx.stacked
+        sums, *rest = ctx.saved_tensors
+        imgs = rest[:S]
+        B = imgs[0].shape[0]
+        if stacked:
+            both = rest[S:2 * S]
+            wl, wr = [t[:B] for t in both], [t[B:] for t in both]
+            gboth = [torch.empty_like(t) for t in both]
+            gl, gr = [t[:B] for t in gboth], [t[B:] for t in gboth]
+        else:
+            wl, wr = rest[S:2 * S], rest[2 * S:3 * S]
+            gl, gr = [torch.empty_like(t) for t in wl], [torch.empty_like(t) for t in wr]
+        lv = _levels(PhotoLevel, S)
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), None, None, None, None,
+                               gl[s].data_ptr(), gr[s].data_ptr(), H, W)
+        g_pixel = torch.zeros_like(sums[0, :, 0]) if g_pixel is None else g_pixel.contiguous()
+        g_ssim = torch.zeros_like(sums[0, :, 0]) if g_ssim is None else g_ssim.contiguous()
+        with torch.cuda.device_of(sums):
+            _lib.call('uof_photo_loss_bwd', lv, S, B, _p(sums), _p(g_pixel), _p(g_ssim), _stream(sums))
+        if stacked:
+            return (None, None, None, *([None] * S), *gboth)
+        return (None, None, None, *([None] * S), *gl, *gr)
+
+
+def _unpack_photo(outs, S, return_diffs):
+    res = (outs[0], outs[1], list(outs[2:2 + S]), list(outs[2 + S:2 + 2 * S]))
+    if return_diffs:
+        res += (list(outs[2 + 2 * S:2 + 3 * S]), list(outs[2 + 3 * S:2 + 4 * S]))
+    return res
+
+
+def photometric_losses(img_pyramid, warped_from_l, warped_from_r, num_scales=3, return_diffs=False):
+    """Fused photometric path of Model_flow.forward (model_flow_paper.py:240-245).
+
+    Returns (loss_pixel (B,), loss_ssim (B,), weight_bwd list, weight_fwd list[, diff_bwd, diff_fwd]):
+    "bwd" pairs with the left image, "fwd" with the right one, as in the reference."""
+    S = num_scales
+    _require_cuda(*img_pyramid[:S], *warped_from_l[:S], *warped_from_r[:S])
+    outs = _PhotoLoss.apply(S, bool(return_diffs), False, *img_pyramid[:S], *warped_from_l[:S], *warped_from_r[:S])
+    return _unpack_photo(outs, S, return_diffs)
+
+
+def photometric_losses_stacked(img_pyramid, warped_lr, num_scales=3, return_diffs=False):
+    """Same, with the two warped pyramids stacked along the batch: warped_lr[s] = (2B,3,H,W)."""
+    S = num_scales
+    _require_cuda(*img_pyramid[:S], *warped_lr[:S])
+    outs = _PhotoLoss.apply(S, bool(return_diffs), True, *img_pyramid[:S], *warped_lr[:S])
+    return _unpack_photo(outs, S, return_diffs)
+
+
+# ------------------------------------------------------------------------------------------ a7
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S, *tensors):
+        flows = [t.contiguous() for t in tensors[:S]]
+        imgs = [t.contiguous() for t in tensors[S:2 * S]]
+        B, Bimg = flows[0].shape[0], imgs[0].shape[0]
+        dev = flows[0].device
+        lv = _levels(SmoothLevel, S)
+        for s in range(S):
+            _, _, H, W = flows[s].shape
+            assert imgs[s].shape[2:] == flows[s].shape[2:]
+            lv[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), None, H, W)
+        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        with torch.cuda.device_of(flows[0]):
+            _lib.call('uof_smooth_loss_fwd', lv, S, B, Bimg, _p(sums), _p(loss), _stream(flows[0]))
+        ctx.save_for_backward(*flows, *imgs)
+        ctx.S = S
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        S = ctx.S
+        flows, imgs = ctx.saved_tensors[:S], ctx.saved_tensors[S:]
+        B, Bimg = flows[0].shape[0], imgs[0].shape[0]
+        lv = _levels(SmoothLevel, S)
+        gf = [torch.empty_like(t) for t in flows]
+        for s in range(S):
+            _, _, H, W = flows[s].shape
+            lv[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), gf[s].data_ptr(), H, W)
+        g = g.contiguous()
+        with torch.cuda.device_of(g):
+            _lib.call('uof_smooth_loss_bwd', lv, S, B, Bimg, _p(g), _stream(g))
+        return (None, *gf, *([None] * S))
+
+
+def flow_smooth_loss(optical_flows, img_pyramid, num_scales=3):
+    """Drop-in for Model_flow.compute_loss_flow_smooth (model_flow_paper.py:168-177).  The flow batch
+    may be a multiple of the image batch (sample b reads image b % B_img): both directions in one launch."""
+    S = num_scales
+    _require_cuda(*optical_flows[:S], *img_pyramid[:S])
+    return _SmoothLoss.apply(S, *optical_flows[:S], *img_pyramid[:S])
+
+
+# ------------------------------------------------------------------------------------------ a8
+class _ConsisLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S, *tensors):
+        ff = [t.contiguous() for t in tensors[:S]]
+        fb = [t.contiguous() for t in tensors[S:2 * S]]
+        wf = [t.contiguous() for t in tensors[2 * S:3 * S]]
+        B = ff[0].shape[0]
+        dev = ff[0].device
+        lv = _levels(ConsisLevel, S)
+        for s in range(S):
+            _, _, H, W = ff[s].shape
+            lv[s] = ConsisLevel(ff[s].data_ptr(), fb[s].data_ptr(), wf[s].data_ptr(), None, H, W)
+        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        with torch.cuda.device_of(ff[0]):
+            _lib.call('uof_consis_loss_fwd', lv, S, B, _p(sums), _p(loss), _stream(ff[0]))
+        ctx.save_for_backward(sums, *ff, *fb, *wf)
+        ctx.S = S
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        S = ctx.S
+        sums, *rest = ctx.saved_tensors
+        ff, fb, wf = rest[:S], rest[S:2 * S], rest[2 * S:3 * S]
+        B = ff[0].shape[0]
+        lv = _levels(ConsisLevel, S)
+        gf = [torch.empty_like(t) for t in ff]
+        for s in range(S):
+            _, _, H, W = ff[s].shape
+            lv[s] = ConsisLevel(ff[s].data_ptr(), fb[s].data_ptr(), wf[s].data_ptr(), gf[s].data_ptr(), H, W)
+        g = g.contiguous()
+        with torch.cuda.device_of(g):
+            _lib.call('uof_consis_loss_bwd', lv, S, B, _p(sums), _p(g), _stream(g))
+        return (None, *gf, *([None] * (2 * S)))
+
+
+def flow_consis_loss(fwd_flows, bwd_flows, weights_fwd, num_scales=3):
+    """Drop-in for Model_flow.compute_loss_flow_consis (model_flow_paper.py:180-195); gradient reaches
+    the forward flows only (bwd flows and the weight are detached in the reference)."""
+    S = num_scales
+    _require_cuda(*fwd_flows[:S], *bwd_flows[:S], *weights_fwd[:S])
+    return _ConsisLoss.apply(S, *fwd_flows[:S], *[t.detach() for t in bwd_flows[:S]],
+                             *[t.detach() for t in weights_fwd[:S]])
+
+
+# ------------------------------------------------------------------------------------------ a9
+def img_pyramid(img: torch.Tensor, num_pyramid: int):
+    """Drop-in for Model_flow.generate_img_pyramid (model_flow_paper.py:54-60): no gradient.  `img` may be
+    a strided view (e.g. one image of the stacked triplet); only the last dimension must be dense."""
+    _require_cuda(img)
+    img = img.detach()
+    if img.stride(3) != 1:
+        img = img.contiguous()
+    B, C, H, W = img.shape
+    outs = [img]
+    if num_pyramid > 1:
+        lv = [torch.empty((B, C, int(H / 2 ** s), int(W / 2 ** s)), device=img.device) for s in range(1, num_pyramid)]
+        ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
+        with torch.cuda.device_of(img):
+            _lib.call('uof_img_pyramid', _p(img), img.stride(0), img.stride(1), img.stride(2), ptrs, num_pyramid,
+                      B, C, H, W, _stream(img))
+        outs += lv
+    return outs
+
+
+# -------------------------------------------------------------------------------------- a12/a13
+class _Splat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, flow):
+        fc = flow.contiguous()
+        B, H, W, _ = fc.shape
+        uc = u.contiguous() if u is not None else None
+        C = uc.shape[3] if uc is not None else 1
+        out = torch.empty((B, H, W, C), device=fc.device)
+        with torch.cuda.device_of(fc):
+            _lib.call('uof_splat_fwd', _p(uc), _p(fc), _p(out), B, H, W, C, _stream(fc))
+        ctx.save_for_backward(fc, *(() if uc is None else (uc,)))
+        ctx.C = C
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        fc = ctx.saved_tensors[0]
+        uc = ctx.saved_tensors[1] if len(ctx.saved_tensors) > 1 else None
+        B, H, W, _ = fc.shape
+        gu = torch.empty_like(uc) if (uc is not None and ctx.needs_input_grad[0]) else None
+        gf = torch.empty_like(fc) if ctx.needs_input_grad[1] else None
+        if gu is None and gf is None:
+            return None, None
+        with torch.cuda.device_of(fc):
+            _lib.call('uof_splat_bwd', _p(gout.contiguous()), _p(uc), _p(fc), _p(gu), _p(gf), B, H, W, ctx.C, _stream(fc))
+        return gu, gf
+
+
+def transformerFwd(U: torch.Tensor, flo: torch.Tensor, out_size=None) -> torch.Tensor:
+    """Bilinear forward splat, NHWC: out[b,yc,xc,:] += U[b,y,x,:]*w (absent from the reference)."""
+    B, H, W, _ = flo.shape
+    if out_size is not None and tuple(out_size) != (H, W):
+        raise ValueError('transformerFwd: out_size %r must equal the flow size %r' % (tuple(out_size), (H, W)))
+    _require_cuda(U, flo)
+    return _Splat.apply(U, flo)
+
+
+def range_map(flow_nhwc: torch.Tensor) -> torch.Tensor:
+    """transformerFwd(ones, flow): how many source pixels land on each target pixel."""
+    _require_cuda(flow_nhwc)
+    return _Splat.apply(None, flow_nhwc)
+
+
+def occlusion_mask(flow_nhwc: torch.Tensor) -> torch.Tensor:
+    """clamp(range_map, 0, 1), no gradient."""
+    with torch.no_grad():
+        r = _Splat.apply(None, flow_nhwc)
+        with torch.cuda.device_of(r):
+            _lib.call('uof_clamp01', _p(r), r.numel(), _stream(r))
+    return r
+
+
+def splat_targets(flow_nhwc: torch.Tensor) -> torch.Tensor:
+    """(B,H,W,4) int64 flat target indices of the four splat corners, -1 when out of bounds."""
+    _require_cuda(flow_nhwc)
+    fc = flow_nhwc.contiguous()
+    B, H, W, _ = fc.shape
+    idx = torch.empty((B, H, W, 4), device=fc.device, dtype=torch.int64)
+    with torch.cuda.device_of(fc):
+        _lib.call('uof_splat_targets', _p(fc), _p(idx), B, H, W, _stream(fc))
+    return idx
+
+
+def fb_consistency_mask(flow_fwd, flow_rev, alpha=3.0, beta=0.05, align_corners=None):
+    """|f_fwd + warp(f_rev, f_fwd)| < max(alpha, beta*|f_fwd|) -> (B,1,H,W) in {0,1}; no gradient."""
+    _require_cuda(flow_fwd, flow_rev)
+    assert flow_fwd.shape == flow_rev.shape and flow_fwd.shape[1] == 2
+    ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+    ff, fr = flow_fwd.detach().contiguous(), flow_rev.detach().contiguous()
+    B, _, H, W = ff.shape
+    mask = torch.empty((B, 1, H, W), device=ff.device)
+    with torch.cuda.device_of(ff):
+        _lib.call('uof_fb_consistency_mask', _p(ff), _p(fr), _p(mask), B, H, W, float(alpha), float(beta), int(ac), _stream(ff))
+    return mask
