@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — train frame-pairs/s of the Model_flow hot path at 256x832 on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one iteration of the reference's train.py:137-152 (zero_grad, Model_flow.forward on a batch of
+synthetic KITTI-shaped triplets, weighted loss, backward, Adam step) = BASELINE.json configs[1]
+("kitti.yaml flow-mode training step, synthetic 256x832 frame pairs, batch=8, 1xB200 fp32").  Each triplet
+holds 2 frame pairs.  N > 1: one process per GPU, DDP over NCCL, per-GPU batch fixed (weak scaling).
+
+Rank 0 prints ONE JSON line (see the driver contract in the task statement): value = whole-job frame-pairs/s
+with inputs resident in HBM; e2e = the same metric with pinned-host inputs copied in and the loss read back
+inside the timed region; roofline = the dominant hand-written kernel's achieved algorithmic GB/s measured
+with CUDA events around its launches during K extra (instrumented) steps; cpu_baseline = the CPU oracle
+(a port of the reference's PyTorch path) timed on this host's cores on a bounded sample.
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port: the reference
+is pure Python and /root/reference does not exist on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'train frame-pairs/s @256x832'
+UNIT = 'frame-pairs/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=8, help='triplets per GPU (kitti.yaml / train.py:168 default 8)')
+    ap.add_argument('--hw', type=int, nargs=2, default=[256, 832])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-profile', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--profile-step', action='store_true',
+                    help='warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(',') for r in open(self.tmp.name).read().strip().splitlines() if r.count(',') >= 8]
+        os.unlink(self.tmp.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].strip().lower() == 'active' for r in rows)]
+        out.update(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=float(rows[0][2]), reasons=reasons,
+                   samples=len(rows), power_w_max=max(float(r[3]) for r in rows))
+        return out
+
+
+# ------------------------------------------------------------------------- per-kernel roofline
+def algorithmic_bytes(name, args):
+    """SURVEY.md 8(d) per-unit figures x the units of this call (fp32).  args = the ctypes call arguments."""
+    def lv_pixels(levels, n, B):
+        return sum(B * levels[i].H * levels[i].W for i in range(n))
+    if name == 'uof_cost_volume_fwd':
+        B, C, H, W = args[3:7]
+        return (2 * C + 81) * 4 * B * H * W
+    if name == 'uof_cost_volume_bwd':
+        B, C, H, W = args[6:10]
+        return (4 * C + 81) * 4 * B * H * W
+    if name == 'uof_warp_fwd':
+        B, C, H, W = args[3:7]
+        return (2 * C + 2) * 4 * B * H * W
+    if name == 'uof_warp_bwd':
+        B, C, H, W = args[5:9]
+        need_gx = bool(args[3].value)
+        return ((3 * C + 4) if need_gx else (2 * C + 4)) * 4 * B * H * W
+    if name == 'uof_photo_loss_fwd':
+        return 36 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_photo_loss_bwd':
+        return 60 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_smooth_loss_fwd':
+        return 20 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_smooth_loss_bwd':
+        return 28 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_consis_loss_fwd':
+        return 20 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_consis_loss_bwd':
+        return 28 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_img_pyramid':
+        B, C, H, W = args[6:10]
+        return int(B * C * H * W * 4 * (1 + 1 / 4 + 1 / 16))
+    return 0
+
+
+class KernelObserver:
+    """Brackets every libuof_b200 call with CUDA events on the launching stream."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.records = []
+
+    def begin(self, name, args):
+        s = self.torch.cuda.current_stream()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        key = name
+        if name.startswith('uof_cost_volume') or name.startswith('uof_warp'):
+            dims = args[3:7] if name.endswith('fwd') else (args[6:10] if 'cost' in name else args[5:9])
+            key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))
+            if name == 'uof_warp_bwd':
+                key += '+gx' if args[3].value else ''
+        e0.record(s)
+        return (key, algorithmic_bytes(name, args), e0, e1, s)
+
+    def end(self, token):
+        key, nbytes, e0, e1, s = token
+        e1.record(s)
+        self.records.append((key, nbytes, e0, e1))
+
+    def summary(self, peak_gbs):
+        self.torch.cuda.synchronize()
+        agg = {}
+        for key, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(key, {'calls': 0, 'ms': 0.0, 'bytes': 0})
+            a['calls'] += 1
+            a['ms'] += e0.elapsed_time(e1)
+            a['bytes'] += nbytes
+        out = []
+        for key, a in agg.items():
+            us = 1e3 * a['ms'] / a['calls']
+            gbs = (a['bytes'] / a['calls']) / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            out.append({'kernel': key, 'calls': a['calls'], 'avg_us': round(us, 2), 'total_ms': round(a['ms'], 3),
+                        'alg_mb': round(a['bytes'] / a['calls'] / 1e6, 3), 'achieved_gbs': round(gbs, 1),
+                        'frac': round(gbs / peak_gbs, 4)})
+        out.sort(key=lambda r: -r['total_ms'])
+        return out
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def cpu_reference_steps(steps, warmup, H, W, sample_batch=1):
+    """The reference's CPU path (oracle port of Model_flow + train.py:137-152) on this host's cores."""
+    import torch
+    from oracle import model as omodel
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.manual_seed(0)
+    model = omodel.Model_flow(omodel.Cfg)
+    opt = omodel.make_optimizer(model)
+    gen = torch.Generator().manual_seed(1234)
+    xs = [torch.rand(sample_batch, 3, 3 * H, W, generator=gen) for _ in range(2)]
+    for i in range(warmup):
+        omodel.train_step(model, opt, xs[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        omodel.train_step(model, opt, xs[i % 2])
+    dt = time.perf_counter() - t0
+    return dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    H, W = args.hw
+    sample = 1
+    s_per_step, cores = cpu_reference_steps(args.steps, args.warmup, H, W, sample)
+    value = 2.0 * sample / s_per_step
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': round(value, 4), 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(1e3 * s_per_step, 3),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam), synthetic 256x832 triplets',
+                   'img_hw': [H, W], 'batch_per_gpu': args.batch, 'frame_pairs_per_triplet': 2},
+        'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': 'each step = 1 triplet (of the batch of %d) through the CPU oracle port of the '
+                                   'reference PyTorch path: fwd+bwd+Adam, %d torch threads' % (args.batch, cores)},
+        'e2e': {'value': round(value, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback for the product path)'
+    torch.backends.cudnn.allow_tf32 = False          # FP32 parity with the reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    import unopticalflow_b200 as u
+    from unopticalflow_b200 import _lib, train as T
+    _lib.load()
+    cfg = T.KITTI_CFG
+    H, W = args.hw
+    B = args.batch
+    weights = T.generate_loss_weights_dict(cfg)
+
+    torch.manual_seed(0)
+    model = u.Model_flow(cfg).to(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=8, broadcast_buffers=False)
+    opt = T.make_optimizer(model, cfg.lr)
+
+    # synthetic KITTI-shaped triplets; NBUF distinct resident batches (> L2 in total) are rotated so that no
+    # timed iteration re-reads inputs left in L2 by the previous one (the step's activations are GBs anyway)
+    NBUF = 4
+    gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    host = [torch.rand(B, 3, 3 * H, W, generator=gen).pin_memory() for _ in range(NBUF)]
+    resident = [h.to(dev) for h in host]
+    in_bytes = host[0].numel() * 4
+
+    def step(x):
+        return T.train_step(net, opt, x, weights)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % NBUF])
+
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
+    # ---- device-resident timing ("value") -----------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms_step = timed(lambda i: step(resident[i % NBUF]), args.steps)
+    launches = (_lib.launch_count() - n0) * world
+    clocks = sampler.stop() if sampler else {}
+
+    # ---- end to end: pinned host inputs -> H2D every step, loss read back every step ---------------
+    last = {}
+
+    def e2e_step(i):
+        x = host[i % NBUF].to(dev, non_blocking=True)
+        last['loss'] = float(step(x))          # .item(): D2H + sync, like the reference's logging path
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- instrumented pass: CUDA events around every hand-written kernel launch ---------------------
+    peak, peak_src = measured_peak_gbs()
+    kernels = []
+    if not args.no_kernel_profile:
+        obs = KernelObserver(torch)
+        _lib.call_observer = obs
+        for i in range(args.steps):
+            step(resident[i % NBUF])
+        _lib.call_observer = None
+        kernels = obs.summary(peak)
+
+    if world > 1:
+        dist.barrier()
+    fp_per_step = 2 * B * world
+    if rank == 0:
+        dominant = kernels[0] if kernels else None
+        own_ms = sum(k['total_ms'] for k in kernels) / max(args.steps, 1)
+        line = {
+            'metric': METRIC, 'value': round(fp_per_step / (ms_step * 1e-3), 3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_step, 3),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam), synthetic 256x832 triplets',
+                       'img_hw': [H, W], 'batch_per_gpu': B, 'global_batch': B * world, 'frame_pairs_per_triplet': 2,
+                       'triplets_per_s': round(B * world / (ms_step * 1e-3), 3),
+                       'parallelism': 'ddp%d' % world if world > 1 else 'single', 'tf32': False,
+                       'l2': '%d distinct resident input batches (%.0f MB total > 126 MB L2) rotated; step working set is GBs'
+                             % (NBUF, NBUF * in_bytes / 1e6)},
+            'clocks': clocks,
+            'e2e': {'value': round(fp_per_step / (ms_e2e * 1e-3), 3), 'unit': UNIT, 'ms_per_step': round(ms_e2e, 3),
+                    'h2d_bytes_per_step': in_bytes * world, 'd2h_bytes_per_step': 4 * world,
+                    'api': 'unopticalflow_b200.train.train_step(Model_flow, Adam, pinned-host batch)'},
+            'gpu_launches': int(launches),
+            'own_kernels_ms_per_step': round(own_ms, 3),
+        }
+        if dominant:
+            line['roofline'] = {'kernel': dominant['kernel'], 'bound': 'hbm', 'achieved': dominant['achieved_gbs'],
+                                'peak': peak, 'unit': 'GB/s', 'frac': dominant['frac'], 'traffic': None,
+                                'peak_source': peak_src, 'alg_bytes_per_launch': int(dominant['alg_mb'] * 1e6),
+                                'avg_us': dominant['avg_us'],
+                                'how': 'CUDA events around each launch during %d instrumented steps' % args.steps}
+            line['kernels'] = kernels[:24]
+        if world == 1 and not args.no_cpu_baseline:
+            s_per_step, cores = cpu_reference_steps(3, 1, H, W, 1)
+            line['cpu_baseline'] = {'value': round(2.0 / s_per_step, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': '3 timed steps (1 warm-up) of 1 triplet (of the batch of %d) through the CPU '
+                                              'oracle port: fwd+bwd+Adam, %.2f s/step' % (B, s_per_step)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

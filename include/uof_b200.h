@@ -36,7 +36,7 @@ typedef void* uof_stream_t;        /* cudaStream_t */
 /* library / diagnostics --------------------------------------------------------------- */
 int uof_abi_version(void);
 const char* uof_last_error(void);
-/* number of kernel launches (incl. memsets) this library has enqueued since load */
+/* number of kernels (memsets not counted) this library has enqueued since load */
 long long uof_launch_count(void);
 
 /* a1: cost volume.  Replaces PWC_tf.corr_naive (pwc_tf.py:97-106):

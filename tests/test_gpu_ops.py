@@ -146,7 +146,8 @@ def test_warp_zero_flow_full_size(U):
     assert int(valid.sum()) == 2 * 254 * 830
     assert bool(valid[:, 1:-1, 1:-1].all())
     ident = U.warp_flow(x, z, use_mask=True, align_corners=True)
-    assert_close(ident, x, 1e-6)
+    # identity up to the fp32 rounding of the normalise/un-normalise round trip (~5e-5 px at x~800)
+    assert_close(ident, x, 2e-4)
 
 
 def test_warp_mask_agreement_full_size(U):

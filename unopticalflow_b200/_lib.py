@@ -91,10 +91,20 @@ def load(path: str | None = None):
     return lib
 
 
+# Optional observer used by bench.py to bracket every C-ABI call with CUDA events: an object with
+# begin(name, args) -> token and end(token).  None in normal operation.
+call_observer = None
+
+
 def call(name: str, *args):
     """Invoke an entry point; non-zero status becomes a Python exception (SURVEY 8b conventions)."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if call_observer is not None:
+        token = call_observer.begin(name, args)
+        rc = getattr(lib, name)(*args)
+        call_observer.end(token)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.uof_last_error().decode('utf-8', 'replace')
         if rc == 1:

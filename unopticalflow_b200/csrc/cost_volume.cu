@@ -291,7 +291,6 @@ extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
   if (ksplit > 1) {
     UOF_CUDA(cudaMemset2DAsync(out, out_batch_stride * sizeof(float), 0,
                                (size_t)UOF_NUM_DISPLACEMENTS * H * W * sizeof(float), B, stream));
-    count_launch();
   }
   dim3 grid(tx, ty, B * ksplit);
   const float inv_c = 1.0f / (float)C;

@@ -323,7 +323,7 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
   smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   smooth_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
-  count_launch(3);
+  count_launch(2);
   return check_launch("smooth_loss_fwd");
 }
 
@@ -347,7 +347,7 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
   consis_fwd_kernel<<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   consis_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
-  count_launch(3);
+  count_launch(2);
   return check_launch("consis_loss_fwd");
 }
 

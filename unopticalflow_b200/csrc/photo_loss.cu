@@ -338,7 +338,7 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
   photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
-  count_launch(3);
+  count_launch(2);
   return check_launch("photo_loss_fwd");
 }
 

@@ -214,7 +214,7 @@ extern "C" int uof_splat_fwd(const float* u, const float* flow, float* out, int 
   } else {
     splat_fwd_kernel<false><<<(unsigned)ceil_div_ll(npix * C, 256), 256, 0, stream>>>(u, f2, out, B, H, W, C);
   }
-  count_launch(2);
+  count_launch(1);
   return check_launch("splat_fwd");
 }
 

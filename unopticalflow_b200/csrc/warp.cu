@@ -234,7 +234,6 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
   const size_t xbytes = (size_t)B * C * H * W * sizeof(float);
   if (gx) {
     UOF_CUDA(cudaMemsetAsync(gx, 0, xbytes, stream));
-    count_launch();
   }
   if (!channels_last) {
     const int bx = W >= 256 ? 256 : (W >= 128 ? 128 : (W >= 64 ? 64 : 32));
@@ -245,7 +244,6 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
       warp_bwd_nchw_kernel<false><<<grid, bx, 0, stream>>>(gout, x, flow, gx, gflow, C, H, W, use_mask, align_corners, sx, sy);
   } else {
     UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
-    count_launch();
     const long long npix = (long long)B * H * W, total = npix * (C / 4);
     const unsigned nb = (unsigned)ceil_div_ll(total, 256);
     if (gx)
