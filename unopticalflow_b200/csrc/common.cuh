@@ -71,8 +71,9 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ float sample_coord(float pos, float f, int size, bool align_corners) {
   float v = __fadd_rn(pos, f);
   float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)max(size - 1, 1)), 1.0f);
-  if (align_corners) return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
-  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 2.0f);
+  // (x / 2) == (x * 0.5f) exactly in binary floating point
+  if (align_corners) return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 0.5f);
 }
 // d(ix)/d(flow) for the mapping above.
 inline float coord_scale(int size, bool align_corners) {

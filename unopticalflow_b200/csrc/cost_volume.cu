@@ -61,8 +61,7 @@ __global__ void __launch_bounds__(NT, 2)
 cost_volume_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
                        int C, int H, int W, long long out_bs, int ksplit, float inv_c) {
   extern __shared__ __align__(16) float smem[];
-  float* s1[2] = {smem, smem + S1 + S2};
-  float* s2[2] = {smem + S1, smem + 2 * S1 + S2};
+  constexpr int kStage = S1 + S2;      // stage k: f1 tile at smem + k*kStage, f2 halo tile S1 floats later
 
   const int tid = threadIdx.x;
   const int gx = tid % (TW / PX), ty = (tid / (TW / PX)) % TH, dg = tid / QUADS;
@@ -84,23 +83,23 @@ cost_volume_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f
 #pragma unroll
       for (int p = 0; p < PX; ++p) acc[r][j][p] = 0.0f;
 
-  stage_tile<VEC4, TH, TW>(s1[0], f1b, k_begin * CK, C, H, W, y0, x0, tid);
-  stage_tile<VEC4, HTH, HTW>(s2[0], f2b, k_begin * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
+  stage_tile<VEC4, TH, TW>(smem, f1b, k_begin * CK, C, H, W, y0, x0, tid);
+  stage_tile<VEC4, HTH, HTW>(smem + S1, f2b, k_begin * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
   cp_async_commit();
 
   for (int k = k_begin; k < k_end; ++k) {
     const int cur = (k - k_begin) & 1;
     if (k + 1 < k_end) {
-      stage_tile<VEC4, TH, TW>(s1[cur ^ 1], f1b, (k + 1) * CK, C, H, W, y0, x0, tid);
-      stage_tile<VEC4, HTH, HTW>(s2[cur ^ 1], f2b, (k + 1) * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
+      stage_tile<VEC4, TH, TW>(smem + (cur ^ 1) * kStage, f1b, (k + 1) * CK, C, H, W, y0, x0, tid);
+      stage_tile<VEC4, HTH, HTW>(smem + (cur ^ 1) * kStage + S1, f2b, (k + 1) * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* a_base = s1[cur] + ty * TW + PX * gx;
-    const float* w_base = s2[cur] + (ty + dg * DYG) * HTW + PX * gx;
+    const float* a_base = smem + cur * kStage + ty * TW + PX * gx;
+    const float* w_base = smem + cur * kStage + S1 + (ty + dg * DYG) * HTW + PX * gx;
 #pragma unroll 2
     for (int cc = 0; cc < CK; ++cc) {
       const float4 a4 = *reinterpret_cast<const float4*>(a_base + cc * TH * TW);
@@ -158,8 +157,7 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
                        const float* __restrict__ f2, float* __restrict__ gf1, float* __restrict__ gf2,
                        int C, int H, int W, int tiles_x, int csplit, float inv_c) {
   extern __shared__ __align__(16) float smem[];
-  float* s2[2] = {smem, smem + S2};
-  float* red = smem + 2 * S2;          // [NGROUP][CK][TH][TW]
+  float* red = smem + 2 * S2;          // [NGROUP][CK][TH][TW]; halo stage k lives at smem + k*S2
 
   const int tid = threadIdx.x;
   const int gx = tid % (TW / PX), ty = (tid / (TW / PX)) % TH, dg = tid / QUADS;
@@ -178,7 +176,7 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
   const int y = y0 + ty, x = x0 + PX * gx;
 
   // prefetch the first chunk while the coefficients are gathered
-  stage_tile<VEC4, HTH, HTW>(s2[0], src_b, k_begin * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
+  stage_tile<VEC4, HTH, HTW>(smem, src_b, k_begin * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
   cp_async_commit();
 
   float kc[DYG][ND][PX];
@@ -205,7 +203,7 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
   for (int k = k_begin; k < k_end; ++k) {
     const int cur = (k - k_begin) & 1;
     if (k + 1 < k_end) {
-      stage_tile<VEC4, HTH, HTW>(s2[cur ^ 1], src_b, (k + 1) * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
+      stage_tile<VEC4, HTH, HTW>(smem + (cur ^ 1) * S2, src_b, (k + 1) * CK, C, H, W, y0 - RAD, x0 - RAD, tid);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -213,7 +211,7 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
     }
     __syncthreads();   // stage `cur` landed; previous iteration's reads of `red` are complete
 
-    const float* w_base = s2[cur] + (ty + dg * DYG) * HTW + PX * gx;
+    const float* w_base = smem + cur * S2 + (ty + dg * DYG) * HTW + PX * gx;
 #pragma unroll
     for (int cc = 0; cc < CK; ++cc) {
       float part[PX] = {0.0f, 0.0f, 0.0f, 0.0f};

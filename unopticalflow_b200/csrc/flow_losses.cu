@@ -25,7 +25,18 @@ __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.
 
 // exp(-10 * mean_c |a_c - b_c|)   (model_flow_paper.py:159-160)
 __device__ __forceinline__ float edge_weight(const float* a, const float* b) {
-  return expf(-10.0f * ((fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2])) / 3.0f));
+  return __expf((-10.0f / 3.0f) * (fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2])));
+}
+
+// one pixel of a row (2 flow + 3 image values), zeros outside the image
+__device__ __forceinline__ void load_row(const float* __restrict__ fb, const float* __restrict__ ib, size_t plane, int W,
+                                         int r, int H, int col, bool col_in, float* v) {
+  const bool inb = col_in && r >= 0 && r < H;
+  const size_t off = (size_t)min(max(r, 0), H - 1) * W + max(col, 0);
+  v[0] = inb ? __ldg(fb + off) : 0.0f;
+  v[1] = inb ? __ldg(fb + off + plane) : 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[2 + c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
 }
 
 // --------------------------------------------------------------------------------- smooth fwd
@@ -47,20 +58,21 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
   float im[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};    // image at rows r-1, r
   float sum_x = 0.0f, sum_y = 0.0f;
 
+  float nxt[5];   // next row, prefetched one iteration ahead: flow x2, image x3
+  load_row(fb, ib, plane, W, sc.y0 - 1, H, sc.col, col_in, nxt);
   for (int r = sc.y0 - 1; r <= sc.y1; ++r) {
-    const bool inb = col_in && r >= 0 && r < H;
-    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
       f[1][k] = f[2][k];
-      f[2][k] = inb ? __ldg(fb + off + k * plane) / 20.0f : 0.0f;   // :174 flow/20.0
+      f[2][k] = nxt[k] * 0.05f;   // :174 flow/20.0
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       im[0][c] = im[1][c];
-      im[1][c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
+      im[1][c] = nxt[2 + c];
     }
+    if (r < sc.y1) load_row(fb, ib, plane, W, r + 1, H, sc.col, col_in, nxt);
     // x term centred on (r, col): needs col-1 and col+1 from the neighbouring lanes
     float ir[3];
 #pragma unroll
@@ -127,22 +139,24 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
   float sy[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};    // sy rows m-2, m-1, m   (m = r-1)
   float gxr[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // x-part of the gradient, rows r-2, r-1, r
 
+  float nxt[5];
+  load_row(fb, ib, plane, W, sc.y0 - 2, H, sc.col, col_in, nxt);
   for (int r = sc.y0 - 2; r <= sc.y1 + 1; ++r) {
     const bool inb = col_in && r >= 0 && r < H;
-    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
       f[1][k] = f[2][k];
-      f[2][k] = inb ? __ldg(fb + off + k * plane) / 20.0f : 0.0f;
+      f[2][k] = nxt[k] * 0.05f;
       gxr[0][k] = gxr[1][k];
       gxr[1][k] = gxr[2][k];
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       im[0][c] = im[1][c];
-      im[1][c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
+      im[1][c] = nxt[2 + c];
     }
+    if (r < sc.y1 + 1) load_row(fb, ib, plane, W, r + 1, H, sc.col, col_in, nxt);
     // x part for row r
     float ir[3];
 #pragma unroll
@@ -170,7 +184,7 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
     if (p >= sc.y0 && p < sc.y1 && col_out) {
       const size_t o = (size_t)p * W + sc.col;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) gb[o + k * plane] = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) / 20.0f;
+      for (int k = 0; k < 2; ++k) gb[o + k * plane] = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) * 0.05f;
     }
   }
 }

@@ -6,20 +6,27 @@
 //
 // Design ("marching warp"): a warp owns a strip of 32 image columns (30 or 28 of them outputs, the
 // rest halo) and marches down R rows.  Each lane loads its pixel's 9 values (I, W_l, W_r) straight
-// from global memory (128 B coalesced per plane per row), computes the weights in registers, gets its
-// left/right neighbours with warp shuffles (horizontal 3-tap sums) and keeps a 3-row register ring
-// for the vertical 3-tap sums.  No shared memory, no temporaries in HBM; per-sample reductions are
-// warp-shuffle trees + one fp32 atomic per warp and quantity.  The backward pass chains two such
-// box filters (5x5 footprint) with a second ring.
+// from global memory (128 B coalesced per plane per row, next row prefetched into registers while the
+// current one is processed), computes the weights in registers, gets its left/right neighbours with warp
+// shuffles (horizontal 3-tap sums) and keeps a 3-row register ring (statically indexed: the row loop
+// is unrolled by 3) for the vertical 3-tap sums.  No shared memory, no temporaries in HBM; per-sample
+// reductions are warp-shuffle trees + one fp32 atomic per warp and quantity.  The backward pass
+// chains two such box filters (5x5 footprint) with a second ring.
+//
+// The kernels are instruction-issue bound, not HBM bound (ncu: profiles/): SSIM on 2 directions x 3
+// channels costs ~50 instructions per map and pixel, so the arithmetic is kept lean: SSIM is evaluated
+// on raw 3x3 sums (the 1/9 factors cancel), one reciprocal per map, and the softmax/Gaussian weight
+// pair needs two exp2-based exponentials per pixel (a_l - 0.5 == -(a_r - 0.5)).
 #include "strips.cuh"
 
 namespace uof {
 namespace {
 
-constexpr float C1 = 0.01f * 0.01f;      // ssim.py:5
-constexpr float C2 = 0.03f * 0.03f;      // ssim.py:6
-constexpr float kEps = 1e-12f;           // model_flow_paper.py:97,145
-constexpr float kInv9 = 1.0f / 9.0f;
+constexpr float C1x81 = 81.0f * 0.01f * 0.01f;      // 81 * C1, ssim.py:5
+constexpr float C2x81 = 81.0f * 0.03f * 0.03f;      // 81 * C2, ssim.py:6
+constexpr float kEps = 1e-12f;                      // model_flow_paper.py:97,145
+constexpr float kThird = 1.0f / 3.0f;
+constexpr float kInvSigma2 = 1.0f / 0.03f;          // model_flow_paper.py:126
 constexpr int kWarpsPerBlock = 4;
 
 struct PhotoParams {
@@ -31,29 +38,29 @@ struct PixelWeights {
   float dl, dr, wl, wr;
 };
 
-// model_flow_paper.py:111-129 for one pixel.
-__device__ __forceinline__ PixelWeights pixel_weights(const float* I, const float* L, const float* R) {
+// model_flow_paper.py:111-129 for one pixel.  px = {I0,I1,I2, L0,L1,L2, R0,R1,R2}.
+__device__ __forceinline__ PixelWeights pixel_weights(const float* px) {
   PixelWeights o;
-  o.dl = (fabsf(I[0] - L[0]) + fabsf(I[1] - L[1]) + fabsf(I[2] - L[2])) / 3.0f;
-  o.dr = (fabsf(I[0] - R[0]) + fabsf(I[1] - R[1]) + fabsf(I[2] - R[2])) / 3.0f;
-  const float vl = (L[0] == 0.0f && L[1] == 0.0f && L[2] == 0.0f) ? 0.0f : 1.0f;
-  const float vr = (R[0] == 0.0f && R[1] == 0.0f && R[2] == 0.0f) ? 0.0f : 1.0f;
-  const float mx = fmaxf(o.dl, o.dr);
-  const float el = expf(o.dl - mx), er = expf(o.dr - mx);
-  const float inv = 1.0f / (el + er);
-  const float al = 1.0f - el * inv - 0.5f, ar = 1.0f - er * inv - 0.5f;
-  o.wl = 2.0f * expf(-(al * al) / 0.03f) * vl;
-  o.wr = 2.0f * expf(-(ar * ar) / 0.03f) * vr;
+  o.dl = (fabsf(px[0] - px[3]) + fabsf(px[1] - px[4]) + fabsf(px[2] - px[5])) * kThird;
+  o.dr = (fabsf(px[0] - px[6]) + fabsf(px[1] - px[7]) + fabsf(px[2] - px[8])) * kThird;
+  const float vl = (px[3] == 0.0f && px[4] == 0.0f && px[5] == 0.0f) ? 0.0f : 1.0f;   // :112
+  const float vr = (px[6] == 0.0f && px[7] == 0.0f && px[8] == 0.0f) ? 0.0f : 1.0f;   // :111
+  // 1 - softmax over (dl, dr): the larger difference gets t/(1+t), the smaller 1/(1+t), t = exp(-|dl-dr|);
+  // both are equally far from 0.5, so the Gaussian weight 2*exp(-(a-0.5)^2/0.03) is shared (:120-126)
+  const float t = __expf(-fabsf(o.dl - o.dr));
+  const float h = __fdividef(1.0f, 1.0f + t) - 0.5f;
+  const float g = 2.0f * __expf(-(h * h) * kInvSigma2);
+  o.wl = g * vl;
+  o.wr = g * vr;
   return o;
 }
 
-__device__ __forceinline__ void load_pixel(const uof_photo_level& L, size_t base, size_t plane, bool inb, float* I,
-                                           float* Wl, float* Wr) {
+__device__ __forceinline__ void load_pixel(const uof_photo_level& L, unsigned off, unsigned plane, bool inb, float* px) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    I[c] = inb ? __ldg(L.img + base + c * plane) : 0.0f;
-    Wl[c] = inb ? __ldg(L.warped_l + base + c * plane) : 0.0f;
-    Wr[c] = inb ? __ldg(L.warped_r + base + c * plane) : 0.0f;
+    px[c] = inb ? __ldg(L.img + off + c * plane) : 0.0f;
+    px[3 + c] = inb ? __ldg(L.warped_l + off + c * plane) : 0.0f;
+    px[6 + c] = inb ? __ldg(L.warped_r + off + c * plane) : 0.0f;
   }
 }
 
@@ -68,23 +75,23 @@ __device__ __forceinline__ void hsum_moments(float xv, float yv, float* m) {
   m[4] = fmaf(xr, yr, fmaf(xv, yv, xl * yl));
 }
 
+// SSIM on raw 3x3 sums: with Sx = 9 mu_x etc. every factor of ssim.py:15-16 is scaled by 81, which cancels.
 struct SsimTerms {
-  float mux, muy, A1, A2, B1, B2, S;
+  float Sx, Sy, A1, A2, B1, B2, invD, S;
 };
 
 __device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float* s1, const float* s2) {
   SsimTerms t;
-  t.mux = (s0[0] + s1[0] + s2[0]) * kInv9;
-  t.muy = (s0[1] + s1[1] + s2[1]) * kInv9;
-  const float sxx = (s0[2] + s1[2] + s2[2]) * kInv9;
-  const float syy = (s0[3] + s1[3] + s2[3]) * kInv9;
-  const float sxy = (s0[4] + s1[4] + s2[4]) * kInv9;
-  const float sig_x = sxx - t.mux * t.mux, sig_y = syy - t.muy * t.muy, sig_xy = sxy - t.mux * t.muy;
-  t.A1 = 2.0f * t.mux * t.muy + C1;
-  t.A2 = 2.0f * sig_xy + C2;
-  t.B1 = t.mux * t.mux + t.muy * t.muy + C1;
-  t.B2 = sig_x + sig_y + C2;
-  t.S = (t.A1 * t.A2) / (t.B1 * t.B2);
+  t.Sx = s0[0] + s1[0] + s2[0];
+  t.Sy = s0[1] + s1[1] + s2[1];
+  const float Sxx = s0[2] + s1[2] + s2[2], Syy = s0[3] + s1[3] + s2[3], Sxy = s0[4] + s1[4] + s2[4];
+  const float pxy = t.Sx * t.Sy, pxx = t.Sx * t.Sx, pyy = t.Sy * t.Sy;
+  t.A1 = fmaf(2.0f, pxy, C1x81);
+  t.A2 = fmaf(2.0f, fmaf(9.0f, Sxy, -pxy), C2x81);
+  t.B1 = pxx + pyy + C1x81;
+  t.B2 = fmaf(9.0f, Sxx, -pxx) + fmaf(9.0f, Syy, -pyy) + C2x81;
+  t.invD = __fdividef(1.0f, t.B1 * t.B2);
+  t.S = (t.A1 * t.A2) * t.invD;
   return t;
 }
 
@@ -97,12 +104,13 @@ photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__
   if (!locate_strip<1>(P.T, gw, lane, sc)) return;
   const uof_photo_level& L = P.lv[sc.level];
   const int H = L.H, W = L.W;
-  const size_t plane = (size_t)H * W;
-  const size_t img_base = (size_t)sc.b * 3 * plane, map_base = (size_t)sc.b * plane;
+  const unsigned plane = (unsigned)(H * W);
+  const unsigned img_base = (unsigned)sc.b * 3u * plane, map_base = (unsigned)sc.b * plane;
   const bool col_in = sc.col >= 0 && sc.col < W;
   const bool col_out = col_in && lane >= 1 && lane <= 30;
+  const int colc = max(sc.col, 0);
 
-  float ring[3][2][3][5];   // [row][direction][channel][moment]
+  float ring[3][2][3][5];   // [row slot][direction][channel][moment]
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -113,45 +121,50 @@ photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__
         for (int k = 0; k < 5; ++k) ring[a][d][c][k] = 0.0f;
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-  for (int r = sc.y0 - 1; r <= sc.y1; ++r) {
-    const bool inb = col_in && r >= 0 && r < H;
-    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
-    float I[3], Wl[3], Wr[3];
-    load_pixel(L, img_base + off, plane, inb, I, Wl, Wr);
-    PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
-    if (inb) pw = pixel_weights(I, Wl, Wr);
-    if (inb && col_out && r >= sc.y0 && r < sc.y1) {
-      acc[0] = fmaf(pw.dl, pw.wl, acc[0]);
-      acc[1] += pw.wl;
-      acc[2] = fmaf(pw.dr, pw.wr, acc[2]);
-      acc[3] += pw.wr;
-      if (L.weight_l) L.weight_l[map_base + off] = pw.wl;
-      if (L.weight_r) L.weight_r[map_base + off] = pw.wr;
-      if (L.diff_l) L.diff_l[map_base + off] = pw.dl;
-      if (L.diff_r) L.diff_r[map_base + off] = pw.dr;
-    }
+  const int r_begin = sc.y0 - 1, r_end = sc.y1;
+  float nxt[9];
+  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, col_in && r_begin >= 0, nxt);
+
+  for (int rb = r_begin; rb <= r_end; rb += 3) {
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const float wd = d ? pw.wr : pw.wl;
+    for (int u = 0; u < 3; ++u) {
+      const int r = rb + u;
+      if (r > r_end) break;
+      const bool inb = col_in && r >= 0 && r < H;
+      const unsigned off = (unsigned)max(r, 0) * W + colc;
+      float px[9];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          ring[0][d][c][k] = ring[1][d][c][k];
-          ring[1][d][c][k] = ring[2][d][c][k];
-        }
-        hsum_moments(I[c] * wd, (d ? Wr[c] : Wl[c]) * wd, ring[2][d][c]);
+      for (int k = 0; k < 9; ++k) px[k] = nxt[k];
+      if (r < r_end) load_pixel(L, img_base + (unsigned)min(r + 1, H - 1) * W + colc, plane, col_in && r + 1 < H, nxt);
+
+      PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
+      if (inb) pw = pixel_weights(px);
+      if (inb && col_out && r >= sc.y0 && r < sc.y1) {
+        acc[0] = fmaf(pw.dl, pw.wl, acc[0]);
+        acc[1] += pw.wl;
+        acc[2] = fmaf(pw.dr, pw.wr, acc[2]);
+        acc[3] += pw.wr;
+        if (L.weight_l) L.weight_l[map_base + off] = pw.wl;
+        if (L.weight_r) L.weight_r[map_base + off] = pw.wr;
+        if (L.diff_l) L.diff_l[map_base + off] = pw.dl;
+        if (L.diff_r) L.diff_r[map_base + off] = pw.dr;
       }
-    }
-    const int q = r - 1;   // row whose 3x3 window is now complete
-    if (q >= sc.y0 && col_out) {
 #pragma unroll
-      for (int d = 0; d < 2; ++d)
+      for (int d = 0; d < 2; ++d) {
+        const float wd = d ? pw.wr : pw.wl;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const SsimTerms t = ssim_from_sums(ring[0][d][c], ring[1][d][c], ring[2][d][c]);
-          acc[4 + d] += fminf(fmaxf((1.0f - t.S) * 0.5f, 0.0f), 1.0f);   // model_flow_paper.py:144
-        }
+        for (int c = 0; c < 3; ++c) hsum_moments(px[c] * wd, px[3 + 3 * d + c] * wd, ring[u][d][c]);
+      }
+      // row q = r-1 now has its full 3x3 window (slots (u+1)%3, (u+2)%3, u hold rows q-1, q, q+1)
+      if (r - 1 >= sc.y0 && col_out) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const SsimTerms t = ssim_from_sums(ring[(u + 1) % 3][d][c], ring[(u + 2) % 3][d][c], ring[u][d][c]);
+            acc[4 + d] += __saturatef(fmaf(-0.5f, t.S, 0.5f));   // clamp((1-S)/2, 0, 1), model_flow_paper.py:144
+          }
+      }
     }
   }
   float* dst = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
@@ -181,6 +194,8 @@ __global__ void photo_loss_finalize_kernel(const __grid_constant__ PhotoParams P
 
 // ------------------------------------------------------------------------------------- backward
 // blockIdx.y = direction (0: left/"bwd", 1: right/"fwd").  Output: d loss / d warped_{l,r}.
+//   y = W*w, raw sums Sy, Syy, Sxy over the 3x3 window of q;  S = S(Sx, Sy, Sxx, Syy, Sxy)
+//   dL/dy[p] = sum_{q in N3(p)} gS[q] * ( dS/dSy[q] + 2 y[p] dS/dSyy[q] + x[p] dS/dSxy[q] )
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
                       const float* __restrict__ g_pixel, const float* __restrict__ g_ssim) {
@@ -191,22 +206,23 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
   if (!locate_strip<2>(P.T, gw, lane, sc)) return;
   const uof_photo_level& L = P.lv[sc.level];
   const int H = L.H, W = L.W;
-  const size_t plane = (size_t)H * W;
-  const size_t img_base = (size_t)sc.b * 3 * plane;
+  const unsigned plane = (unsigned)(H * W);
+  const unsigned img_base = (unsigned)sc.b * 3u * plane;
   const bool col_in = sc.col >= 0 && sc.col < W;
   const bool col_out = col_in && lane >= 2 && lane <= 29;
+  const int colc = max(sc.col, 0);
   float* gout = dir ? L.gwarped_r : L.gwarped_l;
 
   const float n = (float)H * (float)W;
   const float* s = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
   const float inv_div = 1.0f / (s[dir ? 3 : 1] / n + kEps);
-  const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;        // d loss / d |I_c - W_c| per unit weight
+  const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;           // d loss / d |I_c - W_c| per unit weight
   const float coef_ss = -0.5f * __ldg(g_ssim + sc.b) * inv_div / (3.0f * n);  // d loss / d S where the clamp passes
 
-  float mom[3][3][5];    // [row][channel][moment]        rows r-2, r-1, r
-  float abc[3][3][3];    // [row][channel][a,b,c] h-sums  rows q-2, q-1, q   (q = r-1)
-  float xy[3][3][2];     // [row][channel][x,y]           rows r-2, r-1, r
-  float wl1[3][4];       // [row][w, l1grad_c0..2]        rows r-2, r-1, r
+  float mom[3][3][5];    // [row slot][channel][moment]         rows r-2, r-1, r
+  float abc[3][3][3];    // [row slot][channel][a,b,c] h-sums   rows q-2, q-1, q   (q = r-1)
+  float xy[3][3][2];     // [row slot][channel][x,y]
+  float wl1[3][4];       // [row slot][w, l1grad_c0..2]
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -221,87 +237,77 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
     for (int k = 0; k < 4; ++k) wl1[a][k] = 0.0f;
   }
 
-  for (int r = sc.y0 - 2; r <= sc.y1 + 1; ++r) {
-    const bool inb = col_in && r >= 0 && r < H;
-    const size_t off = (size_t)max(r, 0) * W + max(sc.col, 0);
-    float I[3], Wl[3], Wr[3];
-    load_pixel(L, img_base + off, plane, inb, I, Wl, Wr);
-    PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
-    if (inb) pw = pixel_weights(I, Wl, Wr);
-    const float wd = dir ? pw.wr : pw.wl;
+  const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
+  float nxt[9];
+  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, col_in && r_begin >= 0, nxt);
 
-    // shift the per-row rings and push row r
+  for (int rb = r_begin; rb <= r_end; rb += 3) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int u = 0; u < 3; ++u) {
+      const int r = rb + u;
+      if (r > r_end) break;
+      // ring slots: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
+      const bool inb = col_in && r >= 0 && r < H;
+      float px[9];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        mom[0][c][k] = mom[1][c][k];
-        mom[1][c][k] = mom[2][c][k];
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        xy[0][c][k] = xy[1][c][k];
-        xy[1][c][k] = xy[2][c][k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      wl1[0][k] = wl1[1][k];
-      wl1[1][k] = wl1[2][k];
-    }
-    wl1[2][0] = wd;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float wc = dir ? Wr[c] : Wl[c];
-      const float df = I[c] - wc;
-      const float sg = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
-      wl1[2][1 + c] = -sg * coef_l1 * wd;          // d(masked L1)/d W_c
-      xy[2][c][0] = I[c] * wd;
-      xy[2][c][1] = wc * wd;
-      hsum_moments(xy[2][c][0], xy[2][c][1], mom[2][c]);
-    }
+      for (int k = 0; k < 9; ++k) px[k] = nxt[k];
+      if (r < r_end) load_pixel(L, img_base + (unsigned)min(max(r + 1, 0), H - 1) * W + colc, plane,
+                                col_in && r + 1 >= 0 && r + 1 < H, nxt);
+      PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
+      if (inb) pw = pixel_weights(px);
+      const float wd = dir ? pw.wr : pw.wl;
 
-    // row q = r-1: SSIM derivative coefficients w.r.t. the pooled (mu_y, E[y^2], E[xy]) at (q, col)
-    const int q = r - 1;
-    if (q >= sc.y0 - 1) {
-      const bool q_in = col_in && q >= 0 && q < H;
+      wl1[u][0] = wd;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float a = 0.0f, bb = 0.0f, cc = 0.0f;
-        if (q_in) {
-          const SsimTerms t = ssim_from_sums(mom[0][c], mom[1][c], mom[2][c]);
-          const float term = (1.0f - t.S) * 0.5f;
-          if (term >= 0.0f && term <= 1.0f) {        // clamp passes gradient on the closed interval
-            const float D = t.B1 * t.B2;
-            const float dN = 2.0f * t.mux * (t.A2 - t.A1);
-            const float dD = 2.0f * t.muy * (t.B2 - t.B1);
-            a = coef_ss * (dN - t.S * dD) / D;
-            bb = coef_ss * (-t.S / t.B2);
-            cc = coef_ss * (2.0f * t.A1 / D);
+        const float wc = dir ? px[6 + c] : px[3 + c];
+        const float df = px[c] - wc;
+        const float sg = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
+        wl1[u][1 + c] = -sg * coef_l1 * wd;          // d(masked L1)/d W_c
+        xy[u][c][0] = px[c] * wd;
+        xy[u][c][1] = wc * wd;
+        hsum_moments(xy[u][c][0], xy[u][c][1], mom[u][c]);
+      }
+
+      // row q = r-1: coefficients of the SSIM derivative w.r.t. the raw sums (Sy, Syy, Sxy) at (q, col)
+      const int q = r - 1;
+      if (q >= sc.y0 - 1) {
+        const bool q_in = col_in && q >= 0 && q < H;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float a = 0.0f, bb = 0.0f, cc = 0.0f;
+          if (q_in) {
+            const SsimTerms t = ssim_from_sums(mom[0][c], mom[1][c], mom[2][c]);
+            const float term = fmaf(-0.5f, t.S, 0.5f);
+            if (term >= 0.0f && term <= 1.0f) {        // clamp passes gradient on the closed interval
+              const float k = coef_ss * t.invD;
+              const float dN = 2.0f * t.Sx * (t.A2 - t.A1);
+              const float dD = 2.0f * t.Sy * (t.B2 - t.B1);
+              a = k * fmaf(-t.S, dD, dN);
+              bb = -9.0f * k * t.S * t.B1;             // dS/dSyy = -9 S / B2 = -9 S B1 / D
+              cc = 18.0f * k * t.A1;                   // dS/dSxy = 18 A1 / D
+            }
           }
+          float* dst = abc[(u + 2) % 3][c];
+          dst[0] = __shfl_up_sync(kFullMask, a, 1) + a + __shfl_down_sync(kFullMask, a, 1);
+          dst[1] = __shfl_up_sync(kFullMask, bb, 1) + bb + __shfl_down_sync(kFullMask, bb, 1);
+          dst[2] = __shfl_up_sync(kFullMask, cc, 1) + cc + __shfl_down_sync(kFullMask, cc, 1);
         }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          abc[0][c][k] = abc[1][c][k];
-          abc[1][c][k] = abc[2][c][k];
-        }
-        abc[2][c][0] = __shfl_up_sync(kFullMask, a, 1) + a + __shfl_down_sync(kFullMask, a, 1);
-        abc[2][c][1] = __shfl_up_sync(kFullMask, bb, 1) + bb + __shfl_down_sync(kFullMask, bb, 1);
-        abc[2][c][2] = __shfl_up_sync(kFullMask, cc, 1) + cc + __shfl_down_sync(kFullMask, cc, 1);
       }
-    }
 
-    // row p = r-2: all nine coefficient neighbours are in the ring
-    const int p = r - 2;
-    if (p >= sc.y0 && p < sc.y1 && col_out) {
-      const size_t o = img_base + (size_t)p * W + sc.col;
+      // row p = r-2: all nine coefficient neighbours are in the ring
+      const int p = r - 2;
+      if (p >= sc.y0 && p < sc.y1 && col_out) {
+        const unsigned o = img_base + (unsigned)p * W + sc.col;
+        const int sp = (u + 1) % 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float A = abc[0][c][0] + abc[1][c][0] + abc[2][c][0];
-        const float Bq = abc[0][c][1] + abc[1][c][1] + abc[2][c][1];
-        const float Cq = abc[0][c][2] + abc[1][c][2] + abc[2][c][2];
-        const float gy = (A + 2.0f * xy[0][c][1] * Bq + xy[0][c][0] * Cq) * kInv9;
-        gout[o + c * plane] = fmaf(gy, wl1[0][0], wl1[0][1 + c]);
+        for (int c = 0; c < 3; ++c) {
+          const float A = abc[0][c][0] + abc[1][c][0] + abc[2][c][0];
+          const float Bq = abc[0][c][1] + abc[1][c][1] + abc[2][c][1];
+          const float Cq = abc[0][c][2] + abc[1][c][2] + abc[2][c][2];
+          const float gy = fmaf(xy[sp][c][0], Cq, fmaf(2.0f * xy[sp][c][1], Bq, A));
+          gout[o + c * plane] = fmaf(gy, wl1[sp][0], wl1[sp][1 + c]);
+        }
       }
     }
   }
@@ -314,6 +320,7 @@ int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int 
   for (int l = 0; l < nlevels; ++l) {
     const uof_photo_level& L = levels[l];
     UOF_REQUIRE(L.img && L.warped_l && L.warped_r && L.H > 0 && L.W > 0, "photo_loss: level %d incomplete", l);
+    UOF_REQUIRE((long long)B * 3 * L.H * L.W < (1ll << 32), "photo_loss: level %d too large for 32-bit offsets", l);
     if (bwd) UOF_REQUIRE(L.gwarped_l && L.gwarped_r, "photo_loss_bwd: level %d has no gradient buffers", l);
     P.lv[l] = L;
     H[l] = L.H;

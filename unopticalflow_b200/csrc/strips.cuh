@@ -34,7 +34,7 @@ __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int la
   return true;
 }
 
-// Host side: choose the strip height so that the launch has >= ~16 warps per SM, then lay out the
+// Host side: choose the strip height so that the launch has >= ~12 warps per SM, then lay out the
 // per-level prefix table.  Returns the total number of warps (strips), or -1 if it overflows.
 inline long long build_strip_table(StripTable& T, const int* H, const int* W, int nlevels, int B, int halo) {
   T.nlevels = nlevels;
@@ -43,7 +43,7 @@ inline long long build_strip_table(StripTable& T, const int* H, const int* W, in
   for (int l = 0; l < nlevels; ++l) px += (long long)B * H[l] * W[l];
   const int outw = 32 - 2 * halo;
   int rows = 32;
-  while (rows > 8 && px / ((long long)outw * rows) < 16ll * kNumSMs) rows >>= 1;
+  while (rows > 8 && px / ((long long)outw * rows) < 12ll * kNumSMs) rows >>= 1;
   T.rows = rows;
   long long total = 0;
   for (int l = 0; l < nlevels; ++l) {
