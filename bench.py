@@ -136,8 +136,8 @@ def algorithmic_bytes(name, args):
     if name == 'uof_consis_loss_bwd':
         return 28 * lv_pixels(args[0], args[1], args[2])
     if name == 'uof_img_pyramid':
-        B, C, H, W = args[6:10]
-        return int(B * C * H * W * 4 * (1 + 1 / 4 + 1 / 16))
+        nimg, B, C, H, W = args[7:12]
+        return int(nimg * B * C * H * W * 4 * (1 + 1 / 4 + 1 / 16))
     return 0
 
 

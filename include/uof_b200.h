@@ -127,11 +127,13 @@ int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, cons
 
 /* a9: image pyramid.  Replaces Model_flow.generate_img_pyramid (model_flow_paper.py:54-60) for
  * levels 1..nlevels-1 (level 0 is the input itself); adaptive_avg_pool2d bin rule
- * [floor(i*H/h), ceil((i+1)*H/h)).  img is addressed with explicit element strides so the
- * vertically stacked triplet (B,3,3H,W) can be read in place. */
-int uof_img_pyramid(const float* img, long long stride_b, long long stride_c, long long stride_h,
-                    float* const* outs /* host array of nlevels-1 device pointers */, int nlevels,
-                    int B, int C, int H, int W, uof_stream_t stream);
+ * [floor(i*H/h), ceil((i+1)*H/h)).  `nimg` images of shape (B,C,H,W) are addressed with explicit element
+ * strides (image, batch, channel, row; columns dense), so the three images of the vertically stacked
+ * triplet (B,3,3H,W) are processed in place by one launch (stride_img = H*W_row_stride).
+ * outs[l] receives level l+1 as a dense (nimg,B,C,h,w) tensor. */
+int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, long long stride_c,
+                    long long stride_h, float* const* outs /* host array of nlevels-1 device pointers */,
+                    int nlevels, int nimg, int B, int C, int H, int W, uof_stream_t stream);
 
 /* a12: forward splat ("transformerFwd").  NOT in the reference.
  * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;

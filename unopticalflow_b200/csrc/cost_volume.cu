@@ -11,7 +11,7 @@
 //   and slides a 12-float register window along dx.
 //   Small pyramid levels split the channel loop over extra CTAs (fp32 atomics into a zeroed
 //   output) so that the grid still covers the 148 SMs.
-#include "common.cuh"
+#include "cost_volume.h"
 
 namespace uof {
 namespace {
@@ -256,19 +256,14 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
   }
 }
 
+// The TMA + mbarrier variants of both kernels live in cost_volume_tma.cu; the cp.async kernels above are the
+// fallback for W % 4 != 0 (levels 8x26 and 4x13 of the 256x832 pyramid) and for UOF_DISABLE_TMA=1.
 constexpr size_t kFwdSmem = 2 * (S1 + S2) * sizeof(float);                       // 57344
 constexpr size_t kBwdSmem = (2 * S2 + NGROUP * CK * TH * TW) * sizeof(float);    // 65536
 
 bool vec4_ok(const void* a, const void* b, const void* c, int W, long long bs) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   return (W % 4 == 0) && (bs % 4 == 0) && al(a) && al(b) && al(c);
-}
-
-// split the channel loop so that small pyramid levels still put >= ~2 CTAs on every SM
-int pick_split(long long ctas, int nchunks) {
-  int s = 1;
-  while (ctas * s < 2 * kNumSMs && s < nchunks) ++s;
-  return s;
 }
 
 }  // namespace
@@ -282,9 +277,11 @@ extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
   UOF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cost_volume_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   UOF_REQUIRE(out_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_fwd: out_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = 0;
+  if (cv::fwd_tma(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);
-  const int ksplit = pick_split((long long)tx * ty * B, nchunks);
+  const int ksplit = cv::pick_split((long long)tx * ty * B, nchunks);
   UOF_REQUIRE((long long)B * ksplit <= 65535, "cost_volume_fwd: batch too large for one launch");
   if (ksplit > 1) {
     UOF_CUDA(cudaMemset2DAsync(out, out_batch_stride * sizeof(float), 0,
@@ -306,9 +303,11 @@ extern "C" int uof_cost_volume_bwd(const float* gout, long long gout_batch_strid
   UOF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cost_volume_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   UOF_REQUIRE(gout_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_bwd: gout_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = 0;
+  if (cv::bwd_tma(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);
-  const int csplit = pick_split((long long)tx * ty * B * 2, nchunks);
+  const int csplit = cv::pick_split((long long)tx * ty * B * 2, nchunks);
   UOF_REQUIRE((long long)B * csplit <= 65535, "cost_volume_bwd: batch too large for one launch");
   dim3 grid(tx * ty, 2, B * csplit);
   const float inv_c = 1.0f / (float)C;

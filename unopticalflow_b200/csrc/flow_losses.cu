@@ -189,7 +189,8 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
   }
 }
 
-int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, int B, int Bimg, int halo, bool bwd) {
+int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, int B, int Bimg, int halo, bool bwd,
+                int blocks_per_sm) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "smooth_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0 && Bimg > 0 && B % Bimg == 0, "smooth_loss: flow batch %d must be a multiple of image batch %d", B, Bimg);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -201,7 +202,7 @@ int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, in
     W[l] = levels[l].W;
   }
   P.Bimg = Bimg;
-  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo) > 0, "smooth_loss: problem too large");
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, 1, blocks_per_sm, kWarpsPerBlock) > 0, "smooth_loss: problem too large");
   return UOF_OK;
 }
 
@@ -211,6 +212,7 @@ struct ConsisParams {
   int warp_begin[UOF_MAX_LEVELS + 1];
   int warps_per_sample[UOF_MAX_LEVELS];
   int nlevels, B;
+  int vec4;          // every plane is a multiple of 4 pixels and every pointer 16-byte aligned
 };
 constexpr int kConsisPxPerWarp = 32 * 8;
 
@@ -225,6 +227,20 @@ __device__ __forceinline__ bool locate_chunk(const ConsisParams& P, int gw, int&
   return true;
 }
 
+// One warp handles kConsisPxPerWarp = 256 pixels of one sample.  VEC = 4: two float4 loads per plane and lane
+// (all ten loads of a lane are issued before any arithmetic); VEC = 1: scalar fallback for planes that are not a
+// multiple of 4 pixels.
+template <int VEC>
+__device__ __forceinline__ void consis_load(const float* __restrict__ base, int p, int plane, float* v) {
+  if (VEC == 4) {
+    const float4 t = (p < plane) ? __ldg(reinterpret_cast<const float4*>(base + p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = (p < plane) ? __ldg(base + p) : 0.0f;
+  }
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ sums) {
   const int lane = threadIdx.x & 31;
@@ -236,16 +252,27 @@ consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ su
   const float* ff = L.flow_fwd + (size_t)b * 2 * plane;
   const float* fb = L.flow_bwd + (size_t)b * 2 * plane;
   const float* wf = L.weight_fwd + (size_t)b * plane;
+  constexpr int NIT = kConsisPxPerWarp / (32 * VEC);
+  float ax[NIT][VEC], ay[NIT][VEC], bx[NIT][VEC], by[NIT][VEC], w[NIT][VEC];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int p = px0 + (it * 32 + lane) * VEC;
+    consis_load<VEC>(ff, p, plane, ax[it]);
+    consis_load<VEC>(ff + plane, p, plane, ay[it]);
+    consis_load<VEC>(fb, p, plane, bx[it]);
+    consis_load<VEC>(fb + plane, p, plane, by[it]);
+    consis_load<VEC>(wf, p, plane, w[it]);
+  }
   float num = 0.0f, den = 0.0f;
 #pragma unroll
-  for (int it = 0; it < kConsisPxPerWarp / 32; ++it) {
-    const int p = px0 + it * 32 + lane;
-    if (p < plane) {
-      const float ax = __ldg(ff + p), ay = __ldg(ff + plane + p);
-      const float bx = __ldg(fb + p), by = __ldg(fb + plane + p);
-      const float occ = 1.0f - __ldg(wf + p);                                  // :187
-      const float na = sqrtf(ax * ax + ay * ay) + kEps, nb = sqrtf(bx * bx + by * by) + kEps;   // :49
-      num = fmaf(fabsf(ax / na + bx / nb) + fabsf(ay / na + by / nb), occ, num);   // :191
+  for (int it = 0; it < NIT; ++it) {
+    const bool live = px0 + (it * 32 + lane) * VEC < plane;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float occ = live ? 1.0f - w[it][v] : 0.0f;                                               // :187
+      const float ia = __fdividef(1.0f, sqrtf(fmaf(ax[it][v], ax[it][v], ay[it][v] * ay[it][v])) + kEps);   // :49
+      const float ib = __fdividef(1.0f, sqrtf(fmaf(bx[it][v], bx[it][v], by[it][v] * by[it][v])) + kEps);
+      num = fmaf(fabsf(fmaf(ax[it][v], ia, bx[it][v] * ib)) + fabsf(fmaf(ay[it][v], ia, by[it][v] * ib)), occ, num);   // :191
       den += occ;
     }
   }
@@ -271,6 +298,7 @@ __global__ void consis_finalize_kernel(const __grid_constant__ ConsisParams P, c
   loss[b] = acc;
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 consis_bwd_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums, const float* __restrict__ g_loss) {
   const int lane = threadIdx.x & 31;
@@ -285,19 +313,41 @@ consis_bwd_kernel(const __grid_constant__ ConsisParams P, const float* __restric
   float* gf = L.gflow_fwd + (size_t)b * 2 * plane;
   const float n = (float)plane;
   const float coef = __ldg(g_loss + b) / (2.0f * n) / (sums[((size_t)level * P.B + b) * 2 + 1] / n + kEps);
+  constexpr int NIT = kConsisPxPerWarp / (32 * VEC);
+  float ax[NIT][VEC], ay[NIT][VEC], bx[NIT][VEC], by[NIT][VEC], w[NIT][VEC];
 #pragma unroll
-  for (int it = 0; it < kConsisPxPerWarp / 32; ++it) {
-    const int p = px0 + it * 32 + lane;
-    if (p < plane) {
-      const float ax = __ldg(ff + p), ay = __ldg(ff + plane + p);
-      const float bx = __ldg(fb + p), by = __ldg(fb + plane + p);
-      const float occ = 1.0f - __ldg(wf + p);
-      const float ra = sqrtf(ax * ax + ay * ay), na = ra + kEps, nb = sqrtf(bx * bx + by * by) + kEps;
-      const float ux = sgn(ax / na + bx / nb) * coef * occ, uy = sgn(ay / na + by / nb) * coef * occ;
+  for (int it = 0; it < NIT; ++it) {
+    const int p = px0 + (it * 32 + lane) * VEC;
+    consis_load<VEC>(ff, p, plane, ax[it]);
+    consis_load<VEC>(ff + plane, p, plane, ay[it]);
+    consis_load<VEC>(fb, p, plane, bx[it]);
+    consis_load<VEC>(fb + plane, p, plane, by[it]);
+    consis_load<VEC>(wf, p, plane, w[it]);
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int p = px0 + (it * 32 + lane) * VEC;
+    if (p >= plane) continue;
+    float gx[VEC], gy[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float occ = 1.0f - w[it][v];
+      const float ra = sqrtf(fmaf(ax[it][v], ax[it][v], ay[it][v] * ay[it][v]));
+      const float ia = __fdividef(1.0f, ra + kEps);
+      const float ib = __fdividef(1.0f, sqrtf(fmaf(bx[it][v], bx[it][v], by[it][v] * by[it][v])) + kEps);
+      const float ux = sgn(fmaf(ax[it][v], ia, bx[it][v] * ib)) * coef * occ;
+      const float uy = sgn(fmaf(ay[it][v], ia, by[it][v] * ib)) * coef * occ;
       // d(a_i/na)/d a_j = delta_ij/na - a_i a_j/(ra*na^2); torch.norm's subgradient at 0 is 0
-      const float k = ra > 0.0f ? (ux * ax + uy * ay) / (ra * na * na) : 0.0f;
-      gf[p] = ux / na - k * ax;
-      gf[plane + p] = uy / na - k * ay;
+      const float k = ra > 0.0f ? (ux * ax[it][v] + uy * ay[it][v]) * ia * ia * __fdividef(1.0f, ra) : 0.0f;
+      gx[v] = fmaf(-k, ax[it][v], ux * ia);
+      gy[v] = fmaf(-k, ay[it][v], uy * ia);
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(gf + p) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+      *reinterpret_cast<float4*>(gf + plane + p) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+    } else {
+      gf[p] = gx[0];
+      gf[plane + p] = gy[0];
     }
   }
 }
@@ -320,6 +370,13 @@ int fill_consis(ConsisParams& P, const uof_consis_level* levels, int nlevels, in
   P.warp_begin[nlevels] = (int)total;
   P.nlevels = nlevels;
   P.B = B;
+  P.vec4 = 1;
+  for (int l = 0; l < nlevels; ++l) {
+    const uof_consis_level& L = levels[l];
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(L.flow_fwd) | reinterpret_cast<uintptr_t>(L.flow_bwd) |
+                           reinterpret_cast<uintptr_t>(L.weight_fwd) | reinterpret_cast<uintptr_t>(L.gflow_fwd);
+    if ((L.H * L.W) % 4 != 0 || (bits & 15u)) P.vec4 = 0;
+  }
   return UOF_OK;
 }
 
@@ -332,7 +389,8 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
                                    uof_stream_t stream_) {
   UOF_REQUIRE(sums && loss, "smooth_loss_fwd: null output");
   SmoothParams P;
-  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false)) return rc;
+  static const int occ = resident_blocks(smooth_fwd_kernel, kWarpsPerBlock * 32);
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false, occ)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
   smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
@@ -345,7 +403,8 @@ extern "C" int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, 
                                    uof_stream_t stream_) {
   UOF_REQUIRE(g_loss, "smooth_loss_bwd: null input");
   SmoothParams P;
-  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 2, true)) return rc;
+  static const int occ = resident_blocks(smooth_bwd_kernel, kWarpsPerBlock * 32);
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 2, true, occ)) return rc;
   smooth_bwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
                       static_cast<cudaStream_t>(stream_)>>>(P, g_loss);
   count_launch();
@@ -359,7 +418,10 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
   if (int rc = fill_consis(P, levels, nlevels, B, false)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
-  consis_fwd_kernel<<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  if (P.vec4)
+    consis_fwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  else
+    consis_fwd_kernel<1><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   consis_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
   count_launch(2);
   return check_launch("consis_loss_fwd");
@@ -370,8 +432,11 @@ extern "C" int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, 
   UOF_REQUIRE(sums && g_loss, "consis_loss_bwd: null input");
   ConsisParams P;
   if (int rc = fill_consis(P, levels, nlevels, B, true)) return rc;
-  consis_bwd_kernel<<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
-                      static_cast<cudaStream_t>(stream_)>>>(P, sums, g_loss);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P.vec4)
+    consis_bwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums, g_loss);
+  else
+    consis_bwd_kernel<1><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums, g_loss);
   count_launch();
   return check_launch("consis_loss_bwd");
 }

@@ -96,7 +96,7 @@ __device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float
 }
 
 // -------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -313,7 +313,7 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
   }
 }
 
-int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd) {
+int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "photo_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0, "photo_loss: bad batch %d", B);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -326,7 +326,8 @@ int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int 
     H[l] = L.H;
     W[l] = L.W;
   }
-  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo) > 0, "photo_loss: problem too large");
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, bwd ? 2 : 1, blocks_per_sm, kWarpsPerBlock) > 0,
+              "photo_loss: problem too large");
   return UOF_OK;
 }
 
@@ -339,7 +340,8 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
                                   float* loss_ssim, uof_stream_t stream_) {
   UOF_REQUIRE(sums && loss_pixel && loss_ssim, "photo_loss_fwd: null output");
   PhotoParams P;
-  if (int rc = fill_params(P, levels, nlevels, B, 1, false)) return rc;
+  static const int occ = resident_blocks(photo_loss_fwd_kernel, kWarpsPerBlock * 32);
+  if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 6 * sizeof(float), stream));
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
@@ -353,7 +355,8 @@ extern "C" int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, in
                                   const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream_) {
   UOF_REQUIRE(sums && g_loss_pixel && g_loss_ssim, "photo_loss_bwd: null input");
   PhotoParams P;
-  if (int rc = fill_params(P, levels, nlevels, B, 2, true)) return rc;
+  static const int occ = resident_blocks(photo_loss_bwd_kernel, kWarpsPerBlock * 32);
+  if (int rc = fill_params(P, levels, nlevels, B, 2, true, occ)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   dim3 grid(ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), 2);
   photo_loss_bwd_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(P, sums, g_loss_pixel, g_loss_ssim);

@@ -1,23 +1,26 @@
 // a9: loss image pyramid.  Replaces Model_flow.generate_img_pyramid,
 // /root/reference/core/networks/model_flow_paper.py:54-60 (adaptive_avg_pool2d per level, no grad).
-// One launch produces every level >= 1; level 0 equals the input.  Bin rule of adaptive_avg_pool2d:
-// rows [floor(i*H/h), ceil((i+1)*H/h)), accumulated row-major then divided by the bin size.  The
-// input is addressed with explicit strides so that each image of the vertically stacked triplet
-// (B,3,3H,W) is read in place (no split copy).
+// One launch produces every level >= 1 of `nimg` vertically stacked images (the triplet (B,3,3H,W) is read
+// in place through explicit strides, no split copy); level 0 equals the input.
+//
+// Fast path (H % 4 == 0, W % 4 == 0, levels <= 3): a thread owns a 4x4 input block, reads it with four
+// coalesced float4 loads and emits the 2x2 level-1 means and the level-2 mean hierarchically -- the input is
+// read exactly once.  General path: adaptive_avg_pool2d bin rule [floor(i*H/h), ceil((i+1)*H/h)), one thread
+// per output element.
 #include "common.cuh"
 
 namespace uof {
 namespace {
 
 struct PyrParams {
-  float* out[UOF_MAX_LEVELS];
+  float* out[UOF_MAX_LEVELS];          // out[l] is (nimg, B, C, h_l, w_l) contiguous
   int h[UOF_MAX_LEVELS], w[UOF_MAX_LEVELS];
   long long begin[UOF_MAX_LEVELS + 1];
-  int nout, B, C, H, W;
-  long long sb, sc, sh;
+  int nout, nimg, B, C, H, W;
+  long long si, sb, sc, sh;            // element strides: image, batch, channel, row
 };
 
-__global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
+__global__ void __launch_bounds__(256) pyramid_generic_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P.begin[P.nout]) return;
   int l = 0;
@@ -25,14 +28,46 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ Py
   long long e = t - P.begin[l];
   const int h = P.h[l], w = P.w[l];
   const int j = (int)(e % w), i = (int)((e / w) % h);
-  const int c = (int)((e / ((long long)w * h)) % P.C), b = (int)(e / ((long long)w * h * P.C));
+  long long r = e / ((long long)w * h);
+  const int c = (int)(r % P.C);
+  r /= P.C;
+  const int b = (int)(r % P.B), im = (int)(r / P.B);
   const int ys = (int)(((long long)i * P.H) / h), ye = (int)((((long long)i + 1) * P.H + h - 1) / h);
   const int xs = (int)(((long long)j * P.W) / w), xe = (int)((((long long)j + 1) * P.W + w - 1) / w);
-  const float* src = img + b * P.sb + c * P.sc;
+  const float* src = img + im * P.si + b * P.sb + c * P.sc;
   float s = 0.0f;
   for (int y = ys; y < ye; ++y)
     for (int x = xs; x < xe; ++x) s += __ldg(src + y * P.sh + x);
   P.out[l][e] = s / (float)((ye - ys) * (xe - xs));
+}
+
+// thread = one 4x4 input block of one (image, batch, channel) plane
+__global__ void __launch_bounds__(256) pyramid_pow2_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
+  const int W4 = P.W >> 2, H4 = P.H >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)P.nimg * P.B * P.C * H4 * W4;
+  if (t >= total) return;
+  const int bx = (int)(t % W4), by = (int)((t / W4) % H4);
+  const long long plane_id = t / ((long long)W4 * H4);          // (im*B + b)*C + c
+  const int c = (int)(plane_id % P.C);
+  const int b = (int)((plane_id / P.C) % P.B), im = (int)(plane_id / ((long long)P.C * P.B));
+  const float* src = img + im * P.si + b * P.sb + c * P.sc + (long long)(4 * by) * P.sh + 4 * bx;
+  float4 r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k] = __ldg(reinterpret_cast<const float4*>(src + k * P.sh));
+  // level 1: 2x2 means, accumulated row-major like adaptive_avg_pool2d
+  const float a00 = ((r[0].x + r[0].y) + r[1].x + r[1].y) * 0.25f, a01 = ((r[0].z + r[0].w) + r[1].z + r[1].w) * 0.25f;
+  const float a10 = ((r[2].x + r[2].y) + r[3].x + r[3].y) * 0.25f, a11 = ((r[2].z + r[2].w) + r[3].z + r[3].w) * 0.25f;
+  const int w1 = P.W >> 1, h1 = P.H >> 1;
+  float* o1 = P.out[0] + plane_id * ((long long)h1 * w1) + (long long)(2 * by) * w1 + 2 * bx;
+  *reinterpret_cast<float2*>(o1) = make_float2(a00, a01);
+  *reinterpret_cast<float2*>(o1 + w1) = make_float2(a10, a11);
+  if (P.nout > 1) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += ((r[k].x + r[k].y) + r[k].z) + r[k].w;
+    P.out[1][plane_id * ((long long)H4 * W4) + (long long)by * W4 + bx] = s * 0.0625f;
+  }
 }
 
 }  // namespace
@@ -40,15 +75,17 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ Py
 
 using namespace uof;
 
-extern "C" int uof_img_pyramid(const float* img, long long stride_b, long long stride_c, long long stride_h,
-                               float* const* outs, int nlevels, int B, int C, int H, int W, uof_stream_t stream_) {
+extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, long long stride_c,
+                               long long stride_h, float* const* outs, int nlevels, int nimg, int B, int C, int H, int W,
+                               uof_stream_t stream_) {
   UOF_REQUIRE(img && outs, "img_pyramid: null pointer");
   UOF_REQUIRE(nlevels >= 2 && nlevels <= UOF_MAX_LEVELS + 1, "img_pyramid: nlevels must be 2..%d", UOF_MAX_LEVELS + 1);
-  UOF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "img_pyramid: bad shape");
+  UOF_REQUIRE(nimg > 0 && B > 0 && C > 0 && H > 0 && W > 0, "img_pyramid: bad shape");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PyrParams P;
   P.nout = nlevels - 1;
-  P.B = B; P.C = C; P.H = H; P.W = W;
-  P.sb = stride_b; P.sc = stride_c; P.sh = stride_h;
+  P.nimg = nimg; P.B = B; P.C = C; P.H = H; P.W = W;
+  P.si = stride_img; P.sb = stride_b; P.sc = stride_c; P.sh = stride_h;
   long long total = 0;
   for (int l = 0; l < P.nout; ++l) {
     const int s = l + 1;
@@ -57,10 +94,17 @@ extern "C" int uof_img_pyramid(const float* img, long long stride_b, long long s
     UOF_REQUIRE(P.h[l] > 0 && P.w[l] > 0 && outs[l], "img_pyramid: level %d is empty", s);
     P.out[l] = outs[l];
     P.begin[l] = total;
-    total += (long long)B * C * P.h[l] * P.w[l];
+    total += (long long)nimg * B * C * P.h[l] * P.w[l];
   }
   P.begin[P.nout] = total;
-  pyramid_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(P, img);
+  const bool strides_ok = (stride_img % 4 == 0) && (stride_b % 4 == 0) && (stride_c % 4 == 0) && (stride_h % 4 == 0) &&
+                          (reinterpret_cast<uintptr_t>(img) & 15u) == 0 && (reinterpret_cast<uintptr_t>(outs[0]) & 7u) == 0;
+  if (H % 4 == 0 && W % 4 == 0 && P.nout <= 2 && strides_ok) {
+    const long long threads = (long long)nimg * B * C * (H / 4) * (W / 4);
+    pyramid_pow2_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, stream>>>(P, img);
+  } else {
+    pyramid_generic_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(P, img);
+  }
   count_launch();
   return check_launch("img_pyramid");
 }

@@ -146,7 +146,8 @@ extern "C" int uof_ssim_fwd(const float* x, const float* y, float* out, int N, i
   UOF_REQUIRE(x && y && out, "ssim_fwd: null pointer");
   UOF_REQUIRE(N > 0 && H > 0 && W > 0, "ssim_fwd: bad shape N=%d H=%d W=%d", N, H, W);
   StripTable T;
-  UOF_REQUIRE(build_strip_table(T, &H, &W, 1, N, 1) > 0, "ssim_fwd: problem too large");
+  static const int occ = resident_blocks(ssim_fwd_kernel, kWarpsPerBlock * 32);
+  UOF_REQUIRE(build_strip_table(T, &H, &W, 1, N, 1, 1, occ, kWarpsPerBlock) > 0, "ssim_fwd: problem too large");
   ssim_fwd_kernel<<<ceil_div(T.warp_begin[1], kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
       T, x, y, out);
   count_launch();
@@ -158,7 +159,8 @@ extern "C" int uof_ssim_bwd(const float* gout, const float* x, const float* y, f
   UOF_REQUIRE(gout && x && y && gx && gy, "ssim_bwd: null pointer");
   UOF_REQUIRE(N > 0 && H > 0 && W > 0, "ssim_bwd: bad shape N=%d H=%d W=%d", N, H, W);
   StripTable T;
-  UOF_REQUIRE(build_strip_table(T, &H, &W, 1, N, 2) > 0, "ssim_bwd: problem too large");
+  static const int occ = resident_blocks(ssim_bwd_kernel, kWarpsPerBlock * 32);
+  UOF_REQUIRE(build_strip_table(T, &H, &W, 1, N, 2, 1, occ, kWarpsPerBlock) > 0, "ssim_bwd: problem too large");
   ssim_bwd_kernel<<<ceil_div(T.warp_begin[1], kWarpsPerBlock), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
       T, gout, x, y, gx, gy);
   count_launch();

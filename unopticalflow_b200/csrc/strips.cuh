@@ -34,29 +34,52 @@ __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int la
   return true;
 }
 
-// Host side: choose the strip height so that the launch has >= ~12 warps per SM, then lay out the
-// per-level prefix table.  Returns the total number of warps (strips), or -1 if it overflows.
-inline long long build_strip_table(StripTable& T, const int* H, const int* W, int nlevels, int B, int halo) {
+// Host side: choose the strip height and lay out the per-level prefix table.
+// The launch runs `grid_mult` x ceil(warps / warps_per_block) blocks on 148 * blocks_per_sm resident slots; the strip
+// height is the one that minimises (number of waves) x (rows + 2*halo), i.e. whole waves with the least halo
+// re-computation (a 1.3-wave launch costs as much as a 2-wave one).  Returns the number of warps, or -1 on overflow.
+inline long long build_strip_table(StripTable& T, const int* H, const int* W, int nlevels, int B, int halo,
+                                   int grid_mult = 1, int blocks_per_sm = 4, int warps_per_block = 4) {
   T.nlevels = nlevels;
   T.B = B;
-  long long px = 0;
-  for (int l = 0; l < nlevels; ++l) px += (long long)B * H[l] * W[l];
   const int outw = 32 - 2 * halo;
-  int rows = 32;
-  while (rows > 8 && px / ((long long)outw * rows) < 12ll * kNumSMs) rows >>= 1;
-  T.rows = rows;
+  const long long slots = (long long)kNumSMs * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+  int best_rows = 8;
+  double best_cost = 1e300;
+  for (int rows = 8; rows <= 64; rows += 4) {
+    long long warps = 0;
+    for (int l = 0; l < nlevels; ++l) warps += (long long)ceil_div(W[l], outw) * ceil_div(H[l], rows) * B;
+    const long long blocks = ceil_div_ll(warps, warps_per_block) * grid_mult;
+    const double cost = (double)ceil_div_ll(blocks, slots) * (double)(rows + 2 * halo);
+    if (cost <= best_cost) {
+      best_cost = cost;
+      best_rows = rows;
+    }
+  }
+  T.rows = best_rows;
   long long total = 0;
   for (int l = 0; l < nlevels; ++l) {
     T.H[l] = H[l];
     T.W[l] = W[l];
     T.strips_x[l] = ceil_div(W[l], outw);
-    T.strips_y[l] = ceil_div(H[l], rows);
+    T.strips_y[l] = ceil_div(H[l], best_rows);
     T.warp_begin[l] = (int)total;
     total += (long long)T.strips_x[l] * T.strips_y[l] * B;
     if (total >= (1ll << 30)) return -1;
   }
   T.warp_begin[nlevels] = (int)total;
   return total;
+}
+
+// Resident blocks per SM of a kernel (cached by the caller in a static).
+template <class K>
+inline int resident_blocks(K kernel, int threads) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) {
+    (void)cudaGetLastError();
+    n = 4;
+  }
+  return n;
 }
 
 }  // namespace uof

@@ -2,14 +2,18 @@
 // Replaces warp_flow, /root/reference/core/networks/structures/net_utils.py:16-54
 // (CPU mesh grid + blocking H2D copy + ~10 elementwise launches + 1-2 grid_sample + 2 index_put_).
 //
-// NCHW kernels ("fat threads"): a thread owns PXT = 4 consecutive pixels of a row and a chunk of CCH
-// channels.  Flow is read with one float4 per component, the four bilinear footprints (indices, weights,
-// mask) are computed once, and then all 16 gathers of a channel are issued back to back (up to 64 loads
-// in flight per thread) -- the first version (one thread per pixel, one dependent round trip per
-// channel) was latency-bound at 10-20 % of HBM bandwidth (profiles/r1_*).  Splitting channels over
-// the grid keeps the 148 SMs busy on the small pyramid levels (8x26 ... 32x104).
+// NCHW kernels: a warp owns a run of 32*PXT consecutive pixels of one image row and a chunk of CCH channels;
+// lane l handles pixels l, l+32, ..., l+32*(PXT-1) of the run.  Every load/store/RED instruction of the warp
+// therefore touches ~32 neighbouring addresses (4-6 sectors), while each thread still has PXT independent
+// footprints and 4*PXT gathers in flight per channel.  History (profiles/): v1 (one pixel per thread, one
+// dependent round trip per channel) was latency-bound at 10-20 % of HBM peak; v2 gave each thread 4
+// *adjacent* pixels, which fixed the latency but made every warp instruction span 512 B (13-25 sectors per
+// request, ncu) -- this version keeps the per-thread parallelism and restores coalescing.  Channels are
+// split over the grid so that the small pyramid levels (8x26 ... 32x104) still fill the 148 SMs.
 // channels_last kernels: one thread per pixel and float4 channel group; each corner read is a contiguous
 // 16 B vector (north star: "coalesced, float4-vectorised NHWC access").
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace uof {
@@ -17,6 +21,7 @@ namespace {
 
 constexpr float kMaskThreshold = 0.9999f;   // net_utils.py:50
 constexpr int CCH = 8;                      // channels per thread (NCHW kernels)
+constexpr int kWarps = 4;                   // warps per block
 
 __device__ __forceinline__ float cover_of(const Bilinear& bl) {
   // grid_sample of a ones image accumulates nw, ne, sw, se in this order
@@ -25,183 +30,169 @@ __device__ __forceinline__ float cover_of(const Bilinear& bl) {
 
 struct Footprint {
   int o00, o01, o10, o11;        // clamped plane offsets of the four corners
-  float w00, w01, w10, w11;      // weights, zero for out-of-bounds corners, already multiplied by the mask
+  float w00, w01, w10, w11;      // weights, zero for out-of-bounds corners
 };
 
-template <int PXT>
-struct ThreadCoord {
-  int b, chunk, y, x0;
+struct RunCoord {
+  int b, chunk, y, x0;           // x0 = first pixel of the warp's run (lane 0, k = 0)
   bool live;
 };
 
-template <int PXT>
-__device__ __forceinline__ ThreadCoord<PXT> locate(long long t, int nchunk, int H, int WQ, int B) {
-  ThreadCoord<PXT> tc;
-  const int xq = (int)(t % WQ);
-  long long r = t / WQ;
-  tc.y = (int)(r % H);
+// warp index -> (batch, channel chunk, row, run of 32*PXT pixels)
+__device__ __forceinline__ RunCoord locate_run(long long gw, int runs_per_row, int H, int nchunk, int B, int run_px) {
+  RunCoord rc;
+  const int run = (int)(gw % runs_per_row);
+  long long r = gw / runs_per_row;
+  rc.y = (int)(r % H);
   r /= H;
-  tc.chunk = (int)(r % nchunk);
-  tc.b = (int)(r / nchunk);
-  tc.x0 = xq * PXT;
-  tc.live = tc.b < B;
-  return tc;
-}
-
-template <int PXT>
-__device__ __forceinline__ void load_flow(const float* __restrict__ fb, size_t plane, int W, int x0, float* fx, float* fy) {
-  if (PXT == 4) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(fb)), b = __ldg(reinterpret_cast<const float4*>(fb + plane));
-    fx[0] = a.x; fx[1] = a.y; fx[2] = a.z; fx[3] = a.w;
-    fy[0] = b.x; fy[1] = b.y; fy[2] = b.z; fy[3] = b.w;
-  } else {
-#pragma unroll
-    for (int p = 0; p < PXT; ++p) {
-      fx[p] = __ldg(fb + p);
-      fy[p] = __ldg(fb + plane + p);
-    }
-  }
+  rc.chunk = (int)(r % nchunk);
+  rc.b = (int)(r / nchunk);
+  rc.x0 = run * run_px;
+  rc.live = rc.b < B;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------- NCHW fwd
 template <int PXT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kWarps * 32)
 warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out, int B, int C,
-                     int H, int W, int nchunk, int use_mask, int align_corners) {
-  const int WQ = W / PXT;
-  const ThreadCoord<PXT> tc = locate<PXT>((long long)blockIdx.x * blockDim.x + threadIdx.x, nchunk, H, WQ, B);
-  if (!tc.live) return;
+                     int H, int W, int nchunk, int runs_per_row, int use_mask, int align_corners) {
+  const int lane = threadIdx.x & 31;
+  const RunCoord rc = locate_run((long long)blockIdx.x * kWarps + (threadIdx.x >> 5), runs_per_row, H, nchunk, B, 32 * PXT);
+  if (!rc.live) return;
   const size_t plane = (size_t)H * W;
-  const size_t pix = (size_t)tc.y * W + tc.x0;
+  const float* fb = flow + (size_t)rc.b * 2 * plane + (size_t)rc.y * W;
   float fx[PXT], fy[PXT];
-  load_flow<PXT>(flow + (size_t)tc.b * 2 * plane + pix, plane, W, tc.x0, fx, fy);
+  bool ok[PXT];
+#pragma unroll
+  for (int k = 0; k < PXT; ++k) {
+    const int px = rc.x0 + 32 * k + lane;
+    ok[k] = px < W;
+    fx[k] = ok[k] ? __ldg(fb + px) : 0.0f;
+    fy[k] = ok[k] ? __ldg(fb + plane + px) : 0.0f;
+  }
   Footprint fp[PXT];
 #pragma unroll
-  for (int p = 0; p < PXT; ++p) {
-    const Bilinear bl = make_bilinear(sample_coord((float)(tc.x0 + p), fx[p], W, align_corners),
-                                      sample_coord((float)tc.y, fy[p], H, align_corners), H, W);
+  for (int k = 0; k < PXT; ++k) {
+    const int px = rc.x0 + 32 * k + lane;
+    const Bilinear bl = make_bilinear(sample_coord((float)px, fx[k], W, align_corners),
+                                      sample_coord((float)rc.y, fy[k], H, align_corners), H, W);
     const float m = (use_mask && cover_of(bl) < kMaskThreshold) ? 0.0f : 1.0f;
     const int xa = min(max(bl.x0, 0), W - 1), xb = min(max(bl.x0 + 1, 0), W - 1);
     const int ya = min(max(bl.y0, 0), H - 1), yb = min(max(bl.y0 + 1, 0), H - 1);
-    fp[p].o00 = ya * W + xa; fp[p].o01 = ya * W + xb; fp[p].o10 = yb * W + xa; fp[p].o11 = yb * W + xb;
+    fp[k].o00 = ya * W + xa; fp[k].o01 = ya * W + xb; fp[k].o10 = yb * W + xa; fp[k].o11 = yb * W + xb;
     // (v*w)*m == v*(w*m) exactly for m in {0,1}
-    fp[p].w00 = bl.w00 * m; fp[p].w01 = bl.w01 * m; fp[p].w10 = bl.w10 * m; fp[p].w11 = bl.w11 * m;
+    fp[k].w00 = bl.w00 * m; fp[k].w01 = bl.w01 * m; fp[k].w10 = bl.w10 * m; fp[k].w11 = bl.w11 * m;
   }
-  const int c0 = tc.chunk * CCH, c1 = min(C, c0 + CCH);
-  const float* xp = x + ((size_t)tc.b * C + c0) * plane;
-  float* op = out + ((size_t)tc.b * C + c0) * plane + pix;
+  const int cch = (C + nchunk - 1) / nchunk;       // channels per thread
+  const int c0 = rc.chunk * cch, c1 = min(C, c0 + cch);
+  const float* xp = x + ((size_t)rc.b * C + c0) * plane;
+  float* op = out + ((size_t)rc.b * C + c0) * plane + (size_t)rc.y * W + rc.x0 + lane;
 #pragma unroll 2
   for (int c = c0; c < c1; ++c, xp += plane, op += plane) {
     float v[PXT][4];
 #pragma unroll
-    for (int p = 0; p < PXT; ++p) {
-      v[p][0] = __ldg(xp + fp[p].o00);
-      v[p][1] = __ldg(xp + fp[p].o01);
-      v[p][2] = __ldg(xp + fp[p].o10);
-      v[p][3] = __ldg(xp + fp[p].o11);
+    for (int k = 0; k < PXT; ++k) {      // clamped offsets are always valid addresses
+      v[k][0] = __ldg(xp + fp[k].o00);
+      v[k][1] = __ldg(xp + fp[k].o01);
+      v[k][2] = __ldg(xp + fp[k].o10);
+      v[k][3] = __ldg(xp + fp[k].o11);
     }
-    float r[PXT];
 #pragma unroll
-    for (int p = 0; p < PXT; ++p)
-      r[p] = fmaf(v[p][3], fp[p].w11, fmaf(v[p][2], fp[p].w10, fmaf(v[p][1], fp[p].w01, v[p][0] * fp[p].w00)));
-    if (PXT == 4) {
-      *reinterpret_cast<float4*>(op) = make_float4(r[0], r[1], r[2], r[3]);
-    } else {
-#pragma unroll
-      for (int p = 0; p < PXT; ++p) op[p] = r[p];
-    }
+    for (int k = 0; k < PXT; ++k)
+      if (ok[k]) op[32 * k] = fmaf(v[k][3], fp[k].w11, fmaf(v[k][2], fp[k].w10, fmaf(v[k][1], fp[k].w01, v[k][0] * fp[k].w00)));
   }
 }
 
 // ---------------------------------------------------------------------------------- NCHW bwd
 // ATOMIC_GFLOW: several channel chunks contribute to the same gflow element (gflow zero-filled by the host).
 template <int PXT, bool NEED_GX, bool ATOMIC_GFLOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kWarps * 32)
 warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x, const float* __restrict__ flow,
                      float* __restrict__ gx, float* __restrict__ gflow, int B, int C, int H, int W, int nchunk,
-                     int use_mask, int align_corners, float sx, float sy) {
-  const int WQ = W / PXT;
-  const ThreadCoord<PXT> tc = locate<PXT>((long long)blockIdx.x * blockDim.x + threadIdx.x, nchunk, H, WQ, B);
-  if (!tc.live) return;
+                     int runs_per_row, int use_mask, int align_corners, float sx, float sy) {
+  const int lane = threadIdx.x & 31;
+  const RunCoord rc = locate_run((long long)blockIdx.x * kWarps + (threadIdx.x >> 5), runs_per_row, H, nchunk, B, 32 * PXT);
+  if (!rc.live) return;
   const size_t plane = (size_t)H * W;
-  const size_t pix = (size_t)tc.y * W + tc.x0;
+  const size_t row = (size_t)rc.y * W;
+  const float* fb = flow + (size_t)rc.b * 2 * plane + row;
   float fx[PXT], fy[PXT];
-  load_flow<PXT>(flow + (size_t)tc.b * 2 * plane + pix, plane, W, tc.x0, fx, fy);
+  bool ok[PXT];
+#pragma unroll
+  for (int k = 0; k < PXT; ++k) {
+    const int px = rc.x0 + 32 * k + lane;
+    ok[k] = px < W;
+    fx[k] = ok[k] ? __ldg(fb + px) : 0.0f;
+    fy[k] = ok[k] ? __ldg(fb + plane + px) : 0.0f;
+  }
   Footprint fp[PXT];
   float ux[PXT], uy[PXT], tx[PXT], ty[PXT], msk[PXT];
-  bool in00[PXT], in01[PXT], in10[PXT], in11[PXT];
+  unsigned inb[PXT];    // bit0..3: corner 00,01,10,11 in bounds
 #pragma unroll
-  for (int p = 0; p < PXT; ++p) {
-    const float ix = sample_coord((float)(tc.x0 + p), fx[p], W, align_corners);
-    const float iy = sample_coord((float)tc.y, fy[p], H, align_corners);
+  for (int k = 0; k < PXT; ++k) {
+    const int px = rc.x0 + 32 * k + lane;
+    const float ix = sample_coord((float)px, fx[k], W, align_corners);
+    const float iy = sample_coord((float)rc.y, fy[k], H, align_corners);
     const Bilinear bl = make_bilinear(ix, iy, H, W);
-    msk[p] = (use_mask && cover_of(bl) < kMaskThreshold) ? 0.0f : 1.0f;
+    msk[k] = (!ok[k] || (use_mask && cover_of(bl) < kMaskThreshold)) ? 0.0f : 1.0f;
     const int xa = min(max(bl.x0, 0), W - 1), xb = min(max(bl.x0 + 1, 0), W - 1);
     const int ya = min(max(bl.y0, 0), H - 1), yb = min(max(bl.y0 + 1, 0), H - 1);
-    fp[p].o00 = ya * W + xa; fp[p].o01 = ya * W + xb; fp[p].o10 = yb * W + xa; fp[p].o11 = yb * W + xb;
-    fp[p].w00 = bl.w00; fp[p].w01 = bl.w01; fp[p].w10 = bl.w10; fp[p].w11 = bl.w11;
-    in00[p] = bl.in00; in01[p] = bl.in01; in10[p] = bl.in10; in11[p] = bl.in11;
-    tx[p] = bl.tx; ty[p] = bl.ty;
-    ux[p] = (floorf(ix) + 1.0f) - ix;
-    uy[p] = (floorf(iy) + 1.0f) - iy;
+    fp[k].o00 = ya * W + xa; fp[k].o01 = ya * W + xb; fp[k].o10 = yb * W + xa; fp[k].o11 = yb * W + xb;
+    fp[k].w00 = bl.w00; fp[k].w01 = bl.w01; fp[k].w10 = bl.w10; fp[k].w11 = bl.w11;
+    inb[k] = (bl.in00 ? 1u : 0u) | (bl.in01 ? 2u : 0u) | (bl.in10 ? 4u : 0u) | (bl.in11 ? 8u : 0u);
+    if (!ok[k]) inb[k] = 0u;
+    tx[k] = bl.tx; ty[k] = bl.ty;
+    ux[k] = (floorf(ix) + 1.0f) - ix;
+    uy[k] = (floorf(iy) + 1.0f) - iy;
   }
-  const int c0 = tc.chunk * CCH, c1 = min(C, c0 + CCH);
-  const float* xp = x + ((size_t)tc.b * C + c0) * plane;
-  const float* gp = gout + ((size_t)tc.b * C + c0) * plane + pix;
-  float* gxp = NEED_GX ? gx + ((size_t)tc.b * C + c0) * plane : nullptr;
+  const int cch = (C + nchunk - 1) / nchunk;       // channels per thread
+  const int c0 = rc.chunk * cch, c1 = min(C, c0 + cch);
+  const float* xp = x + ((size_t)rc.b * C + c0) * plane;
+  const float* gp = gout + ((size_t)rc.b * C + c0) * plane + row + rc.x0 + lane;
+  float* gxp = NEED_GX ? gx + ((size_t)rc.b * C + c0) * plane : nullptr;
   float gix[PXT], giy[PXT];
 #pragma unroll
-  for (int p = 0; p < PXT; ++p) gix[p] = giy[p] = 0.0f;
+  for (int k = 0; k < PXT; ++k) gix[k] = giy[k] = 0.0f;
 #pragma unroll 2
   for (int c = c0; c < c1; ++c, xp += plane, gp += plane) {
-    float g[PXT];
-    if (PXT == 4) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp));
-      g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
-    } else {
+    float g[PXT], v[PXT][4];
 #pragma unroll
-      for (int p = 0; p < PXT; ++p) g[p] = __ldg(gp + p);
-    }
-    float v[PXT][4];
+    for (int k = 0; k < PXT; ++k) g[k] = ok[k] ? __ldg(gp + 32 * k) : 0.0f;
 #pragma unroll
-    for (int p = 0; p < PXT; ++p) {      // clamped addresses are always valid; zero the out-of-bounds corners after
-      v[p][0] = __ldg(xp + fp[p].o00);
-      v[p][1] = __ldg(xp + fp[p].o01);
-      v[p][2] = __ldg(xp + fp[p].o10);
-      v[p][3] = __ldg(xp + fp[p].o11);
+    for (int k = 0; k < PXT; ++k) {
+      v[k][0] = __ldg(xp + fp[k].o00);
+      v[k][1] = __ldg(xp + fp[k].o01);
+      v[k][2] = __ldg(xp + fp[k].o10);
+      v[k][3] = __ldg(xp + fp[k].o11);
     }
 #pragma unroll
-    for (int p = 0; p < PXT; ++p) {
-      const float gm = g[p] * msk[p];
-      const float v00 = in00[p] ? v[p][0] : 0.0f, v01 = in01[p] ? v[p][1] : 0.0f;
-      const float v10 = in10[p] ? v[p][2] : 0.0f, v11 = in11[p] ? v[p][3] : 0.0f;
+    for (int k = 0; k < PXT; ++k) {
+      const float gm = g[k] * msk[k];
+      const float v00 = (inb[k] & 1u) ? v[k][0] : 0.0f, v01 = (inb[k] & 2u) ? v[k][1] : 0.0f;
+      const float v10 = (inb[k] & 4u) ? v[k][2] : 0.0f, v11 = (inb[k] & 8u) ? v[k][3] : 0.0f;
       // d out / d ix and d out / d iy of the bilinear interpolant
-      gix[p] = fmaf(gm, (v01 - v00) * uy[p] + (v11 - v10) * ty[p], gix[p]);
-      giy[p] = fmaf(gm, (v10 - v00) * ux[p] + (v11 - v01) * tx[p], giy[p]);
+      gix[k] = fmaf(gm, (v01 - v00) * uy[k] + (v11 - v10) * ty[k], gix[k]);
+      giy[k] = fmaf(gm, (v10 - v00) * ux[k] + (v11 - v01) * tx[k], giy[k]);
       if (NEED_GX) {
         float* q = gxp + (size_t)(c - c0) * plane;
-        if (in00[p]) atomicAdd(q + fp[p].o00, gm * fp[p].w00);
-        if (in01[p]) atomicAdd(q + fp[p].o01, gm * fp[p].w01);
-        if (in10[p]) atomicAdd(q + fp[p].o10, gm * fp[p].w10);
-        if (in11[p]) atomicAdd(q + fp[p].o11, gm * fp[p].w11);
+        if (inb[k] & 1u) atomicAdd(q + fp[k].o00, gm * fp[k].w00);
+        if (inb[k] & 2u) atomicAdd(q + fp[k].o01, gm * fp[k].w01);
+        if (inb[k] & 4u) atomicAdd(q + fp[k].o10, gm * fp[k].w10);
+        if (inb[k] & 8u) atomicAdd(q + fp[k].o11, gm * fp[k].w11);
       }
     }
   }
-  float* gfb = gflow + (size_t)tc.b * 2 * plane + pix;
-  if (ATOMIC_GFLOW) {
+  float* gfb = gflow + (size_t)rc.b * 2 * plane + row + rc.x0 + lane;
 #pragma unroll
-    for (int p = 0; p < PXT; ++p) {
-      atomicAdd(gfb + p, gix[p] * sx);
-      atomicAdd(gfb + plane + p, giy[p] * sy);
-    }
-  } else if (PXT == 4) {
-    *reinterpret_cast<float4*>(gfb) = make_float4(gix[0] * sx, gix[1] * sx, gix[2] * sx, gix[3] * sx);
-    *reinterpret_cast<float4*>(gfb + plane) = make_float4(giy[0] * sy, giy[1] * sy, giy[2] * sy, giy[3] * sy);
-  } else {
-#pragma unroll
-    for (int p = 0; p < PXT; ++p) {
-      gfb[p] = gix[p] * sx;
-      gfb[plane + p] = giy[p] * sy;
+  for (int k = 0; k < PXT; ++k) {
+    if (!ok[k]) continue;
+    if (ATOMIC_GFLOW) {
+      atomicAdd(gfb + 32 * k, gix[k] * sx);
+      atomicAdd(gfb + plane + 32 * k, giy[k] * sy);
+    } else {
+      gfb[32 * k] = gix[k] * sx;
+      gfb[plane + 32 * k] = giy[k] * sy;
     }
   }
 }
@@ -249,8 +240,8 @@ __device__ __forceinline__ float4 scale4(const float4& a, float s) {
 }
 
 // --------------------------------------------------------------------------- channels_last bwd
-// gx uses 16-byte vector atomics (red.global.add.v4.f32, sm_90+); the per-group partial flow gradients
-// are accumulated with atomicAdd into a zero-filled gflow.
+// gx uses 16-byte vector atomics (sm_90+); the per-group partial flow gradients are accumulated with
+// atomicAdd into a zero-filled gflow.
 template <bool NEED_GX>
 __global__ void __launch_bounds__(256)
 warp_bwd_nhwc_kernel(const float4* __restrict__ gout, const float4* __restrict__ x, const float* __restrict__ flow,
@@ -303,7 +294,26 @@ int check_args(const char* who, const void* a, const void* b, const void* c, int
   return UOF_OK;
 }
 
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// pixels per thread: enough to cover short rows with one run, at most 4
+int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
+// Pixels per thread.  Measured on B200 (profiles/r1_warp_sweep.txt): the forward kernel is fastest with 2, the
+// backward kernel (more registers per pixel, atomics) with 1 -- occupancy beats per-thread ILP there.
+int pick_pxt(int W, bool bwd) {
+  static const int forced = env_int("UOF_WARP_PXT");
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  if (bwd || W <= 32) return 1;
+  return 2;
+}
+
+// Channels per thread (the grid splits C into ceil(C / cch) chunks).
+int pick_cch() {
+  static const int forced = env_int("UOF_WARP_CCH");
+  return forced > 0 ? forced : CCH;
+}
 
 }  // namespace
 }  // namespace uof
@@ -315,14 +325,11 @@ extern "C" int uof_warp_fwd(const float* x, const float* flow, float* out, int B
   if (int rc = check_args("warp_fwd", x, flow, out, B, C, H, W, channels_last)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!channels_last) {
-    const int nchunk = ceil_div(C, CCH);
-    const bool v4 = (W % 4 == 0) && aligned16(flow) && aligned16(out);
-    const long long threads = (long long)B * nchunk * H * (v4 ? W / 4 : W);
-    const unsigned blocks = (unsigned)ceil_div_ll(threads, 128);
-    if (v4)
-      warp_fwd_nchw_kernel<4><<<blocks, 128, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, use_mask, align_corners);
-    else
-      warp_fwd_nchw_kernel<1><<<blocks, 128, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, use_mask, align_corners);
+    const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, false), runs = ceil_div(W, 32 * pxt);
+    const unsigned blocks = (unsigned)ceil_div_ll((long long)B * nchunk * H * runs, kWarps);
+#define UOF_FWD(P) warp_fwd_nchw_kernel<P><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, runs, use_mask, align_corners)
+    if (pxt == 4) UOF_FWD(4); else if (pxt == 2) UOF_FWD(2); else UOF_FWD(1);
+#undef UOF_FWD
   } else {
     const long long npix = (long long)B * H * W, total = npix * (C / 4);
     warp_fwd_nhwc_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(
@@ -335,13 +342,12 @@ extern "C" int uof_warp_fwd(const float* x, const float* flow, float* out, int B
 
 template <int PXT>
 static void launch_bwd_nchw(const float* gout, const float* x, const float* flow, float* gx, float* gflow, int B, int C,
-                            int H, int W, int nchunk, int use_mask, int align_corners, float sx, float sy,
+                            int H, int W, int nchunk, int runs, int use_mask, int align_corners, float sx, float sy,
                             cudaStream_t stream) {
-  const long long threads = (long long)B * nchunk * H * (W / PXT);
-  const unsigned blocks = (unsigned)ceil_div_ll(threads, 128);
-#define UOF_LAUNCH(GX, AT)                                                                                              \
-  warp_bwd_nchw_kernel<PXT, GX, AT><<<blocks, 128, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, use_mask, \
-                                                                align_corners, sx, sy)
+  const unsigned blocks = (unsigned)ceil_div_ll((long long)B * nchunk * H * runs, kWarps);
+#define UOF_LAUNCH(GX, AT)                                                                                        \
+  warp_bwd_nchw_kernel<PXT, GX, AT><<<blocks, kWarps * 32, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, \
+                                                                        runs, use_mask, align_corners, sx, sy)
   if (gx) {
     if (nchunk > 1) UOF_LAUNCH(true, true); else UOF_LAUNCH(true, false);
   } else {
@@ -358,13 +364,14 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
   const float sx = coord_scale(W, align_corners), sy = coord_scale(H, align_corners);
   if (gx) UOF_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * C * H * W * sizeof(float), stream));
   if (!channels_last) {
-    const int nchunk = ceil_div(C, CCH);
+    const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, true), runs = ceil_div(W, 32 * pxt);
     if (nchunk > 1) UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
-    const bool v4 = (W % 4 == 0) && aligned16(flow) && aligned16(gout) && aligned16(gflow);
-    if (v4)
-      launch_bwd_nchw<4>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, use_mask, align_corners, sx, sy, stream);
+    if (pxt == 4)
+      launch_bwd_nchw<4>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);
+    else if (pxt == 2)
+      launch_bwd_nchw<2>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);
     else
-      launch_bwd_nchw<1>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, use_mask, align_corners, sx, sy, stream);
+      launch_bwd_nchw<1>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);
   } else {
     UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
     const long long npix = (long long)B * H * W, total = npix * (C / 4);

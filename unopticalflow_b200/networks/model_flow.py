@@ -106,7 +106,7 @@ class Model_flow(nn.Module):
         f2 = [torch.cat((f[:B], f[2 * B:]), 0) for f in feats]                       # [left   ; right ]
         flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
 
-        pyr_l, pyr_c, pyr_r = ops.img_pyramid(imgl, S), ops.img_pyramid(img, S), ops.img_pyramid(imgr, S)
+        pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)                  # one launch, triplet read in place
         warped = [ops.warp_flow(torch.cat((pyr_l[s], pyr_r[s]), 0), flows[s], use_mask=True,
                                 align_corners=self.align_corners) for s in range(S)]  # [from_l ; from_r]
 

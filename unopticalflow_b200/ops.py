@@ -342,6 +342,14 @@ def flow_consis_loss(fwd_flows, bwd_flows, weights_fwd, num_scales=3):
 
 
 # ------------------------------------------------------------------------------------------ a9
+def _pyramid_launch(base, nimg, stride_img, B, C, H, W, sb, sc, sh, num_pyramid):
+    lv = [torch.empty((nimg, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=base.device) for s in range(1, num_pyramid)]
+    ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
+    with torch.cuda.device_of(base):
+        _lib.call('uof_img_pyramid', _p(base), stride_img, sb, sc, sh, ptrs, num_pyramid, nimg, B, C, H, W, _stream(base))
+    return lv
+
+
 def img_pyramid(img: torch.Tensor, num_pyramid: int):
     """Drop-in for Model_flow.generate_img_pyramid (model_flow_paper.py:54-60): no gradient.  `img` may be
     a strided view (e.g. one image of the stacked triplet); only the last dimension must be dense."""
@@ -352,13 +360,31 @@ def img_pyramid(img: torch.Tensor, num_pyramid: int):
     B, C, H, W = img.shape
     outs = [img]
     if num_pyramid > 1:
-        lv = [torch.empty((B, C, int(H / 2 ** s), int(W / 2 ** s)), device=img.device) for s in range(1, num_pyramid)]
-        ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
-        with torch.cuda.device_of(img):
-            _lib.call('uof_img_pyramid', _p(img), img.stride(0), img.stride(1), img.stride(2), ptrs, num_pyramid,
-                      B, C, H, W, _stream(img))
-        outs += lv
+        lv = _pyramid_launch(img, 1, 0, B, C, H, W, img.stride(0), img.stride(1), img.stride(2), num_pyramid)
+        outs += [t[0] for t in lv]
     return outs
+
+
+def img_pyramid_triplet(inputs: torch.Tensor, num_pyramid: int):
+    """Pyramids of the three vertically stacked images of a training sample (B,3,3H,W) (model_flow_paper.py:206-209,
+    229-231) in ONE launch.  Returns (pyr_l, pyr_c, pyr_r, stacked) where stacked[s] is the dense (3,B,3,h,w) tensor of
+    level s >= 1 (None for level 0, which is a view of the input)."""
+    _require_cuda(inputs)
+    x = inputs.detach()
+    if x.stride(3) != 1:
+        x = x.contiguous()
+    B, C, H3, W = x.shape
+    H = H3 // 3
+    views = [x[:, :, k * H:(k + 1) * H] for k in range(3)]
+    pyr = [[v] for v in views]
+    stacked = [None]
+    if num_pyramid > 1:
+        lv = _pyramid_launch(x, 3, H * x.stride(2), B, C, H, W, x.stride(0), x.stride(1), x.stride(2), num_pyramid)
+        for t in lv:
+            stacked.append(t)
+            for k in range(3):
+                pyr[k].append(t[k])
+    return pyr[0], pyr[1], pyr[2], stacked
 
 
 # -------------------------------------------------------------------------------------- a12/a13
