@@ -64,6 +64,19 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def ncu_traffic_bytes(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, taken from the committed ncu capture
+    (profiles/ncu_traffic.json, written by profiles/make_traffic_json.py from an `ncu` run of `bench.py --profile-step`);
+    None when the capture has no such launch."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        table = json.load(open(p))
+    except Exception:
+        return None
+    v = table.get(kernel_key)
+    return int(v['dram_bytes']) if v else None
+
+
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampler running during the timed region (B200_PROFILING.md)."""
@@ -148,15 +161,20 @@ class KernelObserver:
         self.torch = torch
         self.records = []
 
-    def begin(self, name, args):
-        s = self.torch.cuda.current_stream()
-        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+    @staticmethod
+    def key_of(name, args):
         key = name
         if name.startswith('uof_cost_volume') or name.startswith('uof_warp'):
             dims = args[3:7] if name.endswith('fwd') else (args[6:10] if 'cost' in name else args[5:9])
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))
             if name == 'uof_warp_bwd':
                 key += '+gx' if args[3].value else ''
+        return key
+
+    def begin(self, name, args):
+        s = self.torch.cuda.current_stream()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        key = self.key_of(name, args)
         e0.record(s)
         return (key, algorithmic_bytes(name, args), e0, e1, s)
 
@@ -293,11 +311,26 @@ def run_b200(args):
         step(resident[i % NBUF])
 
     if args.profile_step:
+        class CallRecorder:          # ordered list of C-ABI calls of the profiled step, to align with ncu's launch list
+            def __init__(self):
+                self.keys = []
+
+            def begin(self, name, a):
+                self.keys.append(KernelObserver.key_of(name, a))
+                return None
+
+            def end(self, token):
+                pass
+        rec = CallRecorder()
         torch.cuda.synchronize()
+        _lib.call_observer = rec
         torch.cuda.profiler.start()
         step(resident[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        _lib.call_observer = None
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump(rec.keys, open(os.path.join(ROOT, 'gpurun_out', 'profile_step_calls.json'), 'w'))
         return
 
     # ---- device-resident timing ("value") -----------------------------------------------------
@@ -329,6 +362,14 @@ def run_b200(args):
         _lib.call_observer = None
         kernels = obs.summary(peak)
 
+    # ---- isolated per-kernel timing (CUDA-graph replay over rotating buffer sets > L2), rank 0 of a 1-GPU run ----
+    isolated = []
+    if not args.no_kernel_profile and world == 1:
+        del resident
+        torch.cuda.empty_cache()
+        from unopticalflow_b200 import kernel_bench
+        isolated = kernel_bench.run(peak, B=B, H=H, W=W)
+
     if world > 1:
         dist.barrier()
     fp_per_step = 2 * B * world
@@ -354,11 +395,17 @@ def run_b200(args):
         }
         if dominant:
             line['roofline'] = {'kernel': dominant['kernel'], 'bound': 'hbm', 'achieved': dominant['achieved_gbs'],
-                                'peak': peak, 'unit': 'GB/s', 'frac': dominant['frac'], 'traffic': None,
+                                'peak': peak, 'unit': 'GB/s', 'frac': dominant['frac'],
+                                'traffic': ncu_traffic_bytes(dominant['kernel']),
                                 'peak_source': peak_src, 'alg_bytes_per_launch': int(dominant['alg_mb'] * 1e6),
                                 'avg_us': dominant['avg_us'],
-                                'how': 'CUDA events around each launch during %d instrumented steps' % args.steps}
+                                'how': 'dominant = largest total device time among the hand-written kernels; CUDA events around '
+                                       'each of its launches during %d instrumented steps (stream backlogged, so no host '
+                                       'latency inside the bracket); traffic = ncu dram bytes of the same launch, '
+                                       'profiles/ncu_traffic.json' % args.steps}
             line['kernels'] = kernels[:24]
+        if isolated:
+            line['kernels_isolated'] = isolated
         if world == 1 and not args.no_cpu_baseline:
             s_per_step, cores = cpu_reference_steps(3, 1, H, W, 1)
             line['cpu_baseline'] = {'value': round(2.0 / s_per_step, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -88,6 +88,8 @@ typedef struct {
  * loss_pixel, loss_ssim: (B) out, summed over levels and both directions. */
 int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B,
                        float* sums, float* loss_pixel, float* loss_ssim, uof_stream_t stream);
+/* backward: writes gwarped_l/gwarped_r.  If every level carries weight_l AND weight_r they must hold the maps written
+ * by uof_photo_loss_fwd on the same inputs (the faster "split" kernel reads them); pass NULL to have them recomputed. */
 int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, int B, const float* sums,
                        const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream);
 

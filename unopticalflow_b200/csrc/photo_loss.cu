@@ -313,7 +313,119 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
   }
 }
 
-int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm) {
+// ------------------------------------------------------------------------- backward, split variant
+// Used when the weight maps written by the forward pass are available (the Python layer saves them): one block of
+// six warps per strip, warp = (direction, channel).  A warp loads only I_c, W_dc and w_d (3 instead of 9 values per
+// pixel), skips the weight math entirely and keeps one channel's rings (36 registers instead of 102), so the kernel
+// runs at ~70 registers / 28+ resident warps per SM instead of 151 / 12 -- the fused-direction kernel above was
+// latency/issue bound at 60 % issue utilisation (ncu, profiles/).
+constexpr int kSplitWarps = 6;
+
+__global__ void __launch_bounds__(kSplitWarps * 32)
+photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
+                            const float* __restrict__ g_pixel, const float* __restrict__ g_ssim) {
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;            // 0..5
+  const int dir = role / 3, c = role - 3 * dir;
+  Strip sc;
+  if (!locate_strip<2>(P.T, blockIdx.x, lane, sc)) return;
+  const uof_photo_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const unsigned plane = (unsigned)(H * W);
+  const unsigned ch_base = ((unsigned)sc.b * 3u + (unsigned)c) * plane, map_base = (unsigned)sc.b * plane;
+  const bool col_in = sc.col >= 0 && sc.col < W;
+  const bool col_out = col_in && lane >= 2 && lane <= 29;
+  const int colc = max(sc.col, 0);
+  const float* __restrict__ img = L.img + ch_base;
+  const float* __restrict__ wrp = (dir ? L.warped_r : L.warped_l) + ch_base;
+  const float* __restrict__ wgt = (dir ? L.weight_r : L.weight_l) + map_base;
+  float* __restrict__ gout = (dir ? L.gwarped_r : L.gwarped_l) + ch_base;
+
+  const float n = (float)H * (float)W;
+  const float* s = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
+  const float inv_div = 1.0f / (s[dir ? 3 : 1] / n + kEps);
+  const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;
+  const float coef_ss = -0.5f * __ldg(g_ssim + sc.b) * inv_div / (3.0f * n);
+
+  float mom[3][5], abc[3][3], xy[3][2], wl1[3][2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) mom[a][k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) abc[a][k] = 0.0f;
+    xy[a][0] = xy[a][1] = wl1[a][0] = wl1[a][1] = 0.0f;
+  }
+
+  const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
+  // three rows of (I, W, w) are kept in flight: a row is ~100 instructions of work, far less than a DRAM round trip
+  float pre[3][3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int r = r_begin + u;
+    const bool inb = col_in && r >= 0 && r < H && r <= r_end;
+    const unsigned o = (unsigned)max(r, 0) * W + colc;
+    pre[u][0] = inb ? __ldg(img + o) : 0.0f;
+    pre[u][1] = inb ? __ldg(wrp + o) : 0.0f;
+    pre[u][2] = inb ? __ldg(wgt + o) : 0.0f;
+  }
+  for (int rb = r_begin; rb <= r_end; rb += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int r = rb + u;
+      if (r > r_end) break;
+      // ring slots: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
+      const float vI = pre[u][0], vW = pre[u][1], vw = pre[u][2];
+      {
+        const int rn = r + 3;
+        const bool inb = col_in && rn >= 0 && rn < H && rn <= r_end;
+        const unsigned o = (unsigned)min(max(rn, 0), H - 1) * W + colc;
+        pre[u][0] = inb ? __ldg(img + o) : 0.0f;
+        pre[u][1] = inb ? __ldg(wrp + o) : 0.0f;
+        pre[u][2] = inb ? __ldg(wgt + o) : 0.0f;
+      }
+      const float df = vI - vW;
+      const float sg = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
+      wl1[u][0] = vw;
+      wl1[u][1] = -sg * coef_l1 * vw;
+      xy[u][0] = vI * vw;
+      xy[u][1] = vW * vw;
+      hsum_moments(xy[u][0], xy[u][1], mom[u]);
+
+      const int q = r - 1;
+      if (q >= sc.y0 - 1) {
+        float a = 0.0f, bb = 0.0f, cc = 0.0f;
+        if (col_in && q >= 0 && q < H) {
+          const SsimTerms t = ssim_from_sums(mom[0], mom[1], mom[2]);
+          const float term = fmaf(-0.5f, t.S, 0.5f);
+          if (term >= 0.0f && term <= 1.0f) {
+            const float k = coef_ss * t.invD;
+            a = k * fmaf(-t.S, 2.0f * t.Sy * (t.B2 - t.B1), 2.0f * t.Sx * (t.A2 - t.A1));
+            bb = -9.0f * k * t.S * t.B1;
+            cc = 18.0f * k * t.A1;
+          }
+        }
+        float* dst = abc[(u + 2) % 3];
+        dst[0] = __shfl_up_sync(kFullMask, a, 1) + a + __shfl_down_sync(kFullMask, a, 1);
+        dst[1] = __shfl_up_sync(kFullMask, bb, 1) + bb + __shfl_down_sync(kFullMask, bb, 1);
+        dst[2] = __shfl_up_sync(kFullMask, cc, 1) + cc + __shfl_down_sync(kFullMask, cc, 1);
+      }
+
+      const int p = r - 2;
+      if (p >= sc.y0 && p < sc.y1 && col_out) {
+        const int sp = (u + 1) % 3;
+        const float A = abc[0][0] + abc[1][0] + abc[2][0];
+        const float Bq = abc[0][1] + abc[1][1] + abc[2][1];
+        const float Cq = abc[0][2] + abc[1][2] + abc[2][2];
+        const float gy = fmaf(xy[sp][0], Cq, fmaf(2.0f * xy[sp][1], Bq, A));
+        gout[(unsigned)p * W + sc.col] = fmaf(gy, wl1[sp][0], wl1[sp][1]);
+      }
+    }
+  }
+}
+
+int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm,
+                bool split = false) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "photo_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0, "photo_loss: bad batch %d", B);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -326,7 +438,8 @@ int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int 
     H[l] = L.H;
     W[l] = L.W;
   }
-  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, bwd ? 2 : 1, blocks_per_sm, kWarpsPerBlock) > 0,
+  // split backward: one block per strip; fused backward: two grid rows (directions) of 4-warp blocks
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, (bwd && !split) ? 2 : 1, blocks_per_sm, split ? 1 : kWarpsPerBlock) > 0,
               "photo_loss: problem too large");
   return UOF_OK;
 }
@@ -355,6 +468,16 @@ extern "C" int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, in
                                   const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream_) {
   UOF_REQUIRE(sums && g_loss_pixel && g_loss_ssim, "photo_loss_bwd: null input");
   PhotoParams P;
+  bool have_weights = levels != nullptr && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS;
+  for (int l = 0; have_weights && l < nlevels; ++l) have_weights = levels[l].weight_l && levels[l].weight_r;
+  if (have_weights) {     // weight maps of the forward pass are available: (strip, direction, channel) warps
+    static const int occ_split = resident_blocks(photo_loss_bwd_split_kernel, kSplitWarps * 32);
+    if (int rc = fill_params(P, levels, nlevels, B, 2, true, occ_split, /*split=*/true)) return rc;
+    photo_loss_bwd_split_kernel<<<P.T.warp_begin[nlevels], kSplitWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+        P, sums, g_loss_pixel, g_loss_ssim);
+    count_launch();
+    return check_launch("photo_loss_bwd (split)");
+  }
   static const int occ = resident_blocks(photo_loss_bwd_kernel, kWarpsPerBlock * 32);
   if (int rc = fill_params(P, levels, nlevels, B, 2, true, occ)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

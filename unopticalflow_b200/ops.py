@@ -188,10 +188,11 @@ class _PhotoLoss(torch.autograd.Function):
         loss_pixel, loss_ssim = torch.empty(B, device=dev), torch.empty(B, device=dev)
         with torch.cuda.device_of(imgs[0]):
             _lib.call('uof_photo_loss_fwd', lv, S, B, _p(sums), _p(loss_pixel), _p(loss_ssim), _stream(imgs[0]))
+        # the weight maps are saved too: with them the backward kernel skips the weight math (split variant)
         if stacked:
-            ctx.save_for_backward(sums, *imgs, *both)
+            ctx.save_for_backward(sums, *imgs, *both, *weights_l, *weights_r)
         else:
-            ctx.save_for_backward(sums, *imgs, *wl, *wr)
+            ctx.save_for_backward(sums, *imgs, *wl, *wr, *weights_l, *weights_r)
         ctx.S, ctx.stacked = S, stacked
         outs = (loss_pixel, loss_ssim, *weights_l, *weights_r, *diffs_l, *diffs_r)
         ctx.mark_non_differentiable(*outs[2:])
@@ -208,14 +209,16 @@ class _PhotoLoss(torch.autograd.Function):
             wl, wr = [t[:B] for t in both], [t[B:] for t in both]
             gboth = [torch.empty_like(t) for t in both]
             gl, gr = [t[:B] for t in gboth], [t[B:] for t in gboth]
+            wmaps = rest[2 * S:4 * S]
         else:
             wl, wr = rest[S:2 * S], rest[2 * S:3 * S]
             gl, gr = [torch.empty_like(t) for t in wl], [torch.empty_like(t) for t in wr]
+            wmaps = rest[3 * S:5 * S]
         lv = _levels(PhotoLevel, S)
         for s in range(S):
             _, _, H, W = imgs[s].shape
-            lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), None, None, None, None,
-                               gl[s].data_ptr(), gr[s].data_ptr(), H, W)
+            lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), wmaps[s].data_ptr(),
+                               wmaps[S + s].data_ptr(), None, None, gl[s].data_ptr(), gr[s].data_ptr(), H, W)
         g_pixel = torch.zeros_like(sums[0, :, 0]) if g_pixel is None else g_pixel.contiguous()
         g_ssim = torch.zeros_like(sums[0, :, 0]) if g_ssim is None else g_ssim.contiguous()
         with torch.cuda.device_of(sums):
