@@ -93,6 +93,25 @@ int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B,
 int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, int B, const float* sums,
                        const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream);
 
+/* a4 seam: Model_flow.compute_diff_weight (model_flow_paper.py:101-134) on one pyramid level.
+ * img, warped_*: (B,3,H,W); diff_*, weight_*: (B,1,H,W).  Weights carry no gradient (detached in the reference). */
+int uof_diff_weight_fwd(const float* img, const float* warped_l, const float* warped_r, float* diff_l, float* diff_r,
+                        float* weight_l, float* weight_r, int B, int H, int W, uof_stream_t stream);
+/* g_diff_* (B,1,H,W) may be NULL (treated as zero); gwarped_* (B,3,H,W) are overwritten. */
+int uof_diff_weight_bwd(const float* img, const float* warped_l, const float* warped_r, const float* g_diff_l,
+                        const float* g_diff_r, float* gwarped_l, float* gwarped_r, int B, int H, int W,
+                        uof_stream_t stream);
+
+/* a5 seam: Model_flow.compute_loss_with_mask (model_flow_paper.py:90-99):
+ *   loss[b] = sum_l mean(diff_l * mask_l) / (mean(mask_l) + 1e-12).
+ * diff, mask, H, W: HOST arrays of nlevels entries; diff[l] is (B,C,H,W), mask[l] (B,1,H,W).
+ * sums: (nlevels,B,2) workspace (zero-filled here).  Gradient flows to diff only. */
+int uof_masked_mean_fwd(const float* const* diff, const float* const* mask, const int* H, const int* W, int nlevels,
+                        int B, int C, float* sums, float* loss, uof_stream_t stream);
+int uof_masked_mean_bwd(const float* const* diff, const float* const* mask, float* const* gdiff, const int* H,
+                        const int* W, int nlevels, int B, int C, const float* sums, const float* g_loss,
+                        uof_stream_t stream);
+
 /* a6 seam: SSIM map.  Replaces SSIM(x,y) (pytorch_ssim/ssim.py:4-19) on N = B*C planes. */
 int uof_ssim_fwd(const float* x, const float* y, float* out, int N, int H, int W, uof_stream_t stream);
 int uof_ssim_bwd(const float* gout, const float* x, const float* y, float* gx, float* gy,

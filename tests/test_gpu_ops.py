@@ -396,3 +396,33 @@ def test_fb_consistency_mask(U, ac):
     assert out.shape == (B, 1, H, W)
     assert 0.05 < float(ref.mean()) < 0.95
     assert float((out == ref).float().mean()) >= MASK_AGREE
+
+
+def test_diff_weight_and_masked_mean_seams_with_gradients(U):
+    """a4/a5 seams used one by one (not through the fused kernel): values and gradients w.r.t. the warped images."""
+    g = torch.Generator().manual_seed(31)
+    B, H, W, S = 2, 24, 40, 3
+    pyr, _, _, from_l, from_r = pyramid_case(g, B, H, W, S)
+    wl = [t.clone().requires_grad_(True) for t in from_l]
+    wr = [t.clone().requires_grad_(True) for t in from_r]
+    d_b, d_f, w_b, w_f = O.diff_weight(wl, pyr[1], wr, S)
+    ref = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+    ct = torch.randn(B, generator=g)
+    ref_g = torch.autograd.grad((ref * ct).sum(), wl + wr)
+    cl, cr = [gpu(t, True) for t in from_l], [gpu(t, True) for t in from_r]
+    ci = [t.cuda() for t in pyr[1]]
+    gd_b, gd_f, gw_b, gw_f = U.ops.diff_weight(cl, ci, cr, S)
+    assert not gw_b[0].requires_grad and gd_b[0].requires_grad
+    got = U.ops.loss_with_mask(gd_f, gw_f, S) + U.ops.loss_with_mask(gd_b, gw_b, S)
+    got_g = torch.autograd.grad((got * ct.cuda()).sum(), cl + cr)
+    assert_close(got, ref, REL_TOL, 'masked L1 through the seams')
+    for a, b in zip(got_g, ref_g):
+        assert_close(a, b, REL_TOL, 'd loss / d warped through the seams')
+    # 3-channel diff (compute_loss_pixel-style input) against a 1-channel mask
+    d3 = [torch.rand(B, 3, H >> s, W >> s, generator=g).requires_grad_(True) for s in range(S)]
+    r3 = O.loss_with_mask(d3, w_f, S)
+    c3 = [gpu(t, True) for t in d3]
+    g3 = U.ops.loss_with_mask(c3, [t.cuda() for t in w_f], S)
+    assert_close(g3, r3, REL_TOL)
+    for a, b in zip(torch.autograd.grad(g3.sum(), c3), torch.autograd.grad(r3.sum(), d3)):
+        assert_close(a, b, REL_TOL)

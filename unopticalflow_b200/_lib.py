@@ -43,6 +43,12 @@ SIGNATURES = {
     'uof_warp_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'uof_photo_loss_fwd': [ctypes.POINTER(PhotoLevel), _I, _I, _P, _P, _P, _P],
     'uof_photo_loss_bwd': [ctypes.POINTER(PhotoLevel), _I, _I, _P, _P, _P, _P],
+    'uof_diff_weight_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'uof_diff_weight_bwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'uof_masked_mean_fwd': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_I),
+                            ctypes.POINTER(_I), _I, _I, _I, _P, _P, _P],
+    'uof_masked_mean_bwd': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                            ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _I, _I, _P, _P, _P],
     'uof_ssim_fwd': [_P, _P, _P, _I, _I, _I, _P],
     'uof_ssim_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'uof_smooth_loss_fwd': [ctypes.POINTER(SmoothLevel), _I, _I, _I, _P, _P, _P],

@@ -17,6 +17,8 @@
 // channels costs ~50 instructions per map and pixel, so the arithmetic is kept lean: SSIM is evaluated
 // on raw 3x3 sums (the 1/9 factors cancel), one reciprocal per map, and the softmax/Gaussian weight
 // pair needs two exp2-based exponentials per pixel (a_l - 0.5 == -(a_r - 0.5)).
+#include <stdlib.h>
+
 #include "strips.cuh"
 
 namespace uof {
@@ -424,8 +426,150 @@ photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* 
   }
 }
 
+// ------------------------------------------------------------------- backward, split + pixel-pair variant
+// Same decomposition as the split kernel, but every lane owns TWO adjacent columns (float2 loads/stores, 64
+// columns per warp of which 60 are outputs).  ncu showed the split kernel issue-bound at 161 instructions per
+// warp-row, ~75 of them addressing/predication/control: the pair layout amortises that overhead over two pixels,
+// halves the shuffles per pixel (2 instead of 4 per quantity and pair) and shrinks the column halo from 4/32 to 4/64.
+// Requires even W at every level (pairs are then entirely inside or outside the image).
+__device__ __forceinline__ void pair_moments(float x0, float y0, float x1, float y1, float* m0, float* m1) {
+  const float xl = __shfl_up_sync(kFullMask, x1, 1), yl = __shfl_up_sync(kFullMask, y1, 1);      // left neighbour of px0
+  const float xr = __shfl_down_sync(kFullMask, x0, 1), yr = __shfl_down_sync(kFullMask, y0, 1);  // right neighbour of px1
+  const float sx = x0 + x1, sy = y0 + y1;
+  const float sxx = fmaf(x1, x1, x0 * x0), syy = fmaf(y1, y1, y0 * y0), sxy = fmaf(x1, y1, x0 * y0);
+  m0[0] = sx + xl;            m1[0] = sx + xr;
+  m0[1] = sy + yl;            m1[1] = sy + yr;
+  m0[2] = fmaf(xl, xl, sxx);  m1[2] = fmaf(xr, xr, sxx);
+  m0[3] = fmaf(yl, yl, syy);  m1[3] = fmaf(yr, yr, syy);
+  m0[4] = fmaf(xl, yl, sxy);  m1[4] = fmaf(xr, yr, sxy);
+}
+
+__device__ __forceinline__ void ssim_coeffs(const float* s0, const float* s1, const float* s2, bool live, float coef_ss,
+                                            float* abc) {
+  abc[0] = abc[1] = abc[2] = 0.0f;
+  if (!live) return;
+  const SsimTerms t = ssim_from_sums(s0, s1, s2);
+  const float term = fmaf(-0.5f, t.S, 0.5f);
+  if (term >= 0.0f && term <= 1.0f) {        // clamp passes gradient on the closed interval
+    const float k = coef_ss * t.invD;
+    abc[0] = k * fmaf(-t.S, 2.0f * t.Sy * (t.B2 - t.B1), 2.0f * t.Sx * (t.A2 - t.A1));
+    abc[1] = -9.0f * k * t.S * t.B1;
+    abc[2] = 18.0f * k * t.A1;
+  }
+}
+
+__global__ void __launch_bounds__(kSplitWarps * 32)
+photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
+                           const float* __restrict__ g_pixel, const float* __restrict__ g_ssim) {
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;
+  const int dir = role / 3, c = role - 3 * dir;
+  Strip sc;
+  if (!locate_strip<2, 2>(P.T, blockIdx.x, lane, sc)) return;
+  const uof_photo_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const unsigned plane = (unsigned)(H * W);
+  const bool pin = sc.col >= 0 && sc.col < W;            // W even: the pair is entirely inside or outside
+  const bool pout = pin && lane >= 1 && lane <= 30;
+  const unsigned colc = (unsigned)max(sc.col, 0);
+  const unsigned ch_base = ((unsigned)sc.b * 3u + (unsigned)c) * plane + colc, map_base = (unsigned)sc.b * plane + colc;
+  const float* __restrict__ img = L.img + ch_base;
+  const float* __restrict__ wrp = (dir ? L.warped_r : L.warped_l) + ch_base;
+  const float* __restrict__ wgt = (dir ? L.weight_r : L.weight_l) + map_base;
+  float* __restrict__ gout = (dir ? L.gwarped_r : L.gwarped_l) + ch_base;
+
+  const float n = (float)H * (float)W;
+  const float* s = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
+  const float inv_div = 1.0f / (s[dir ? 3 : 1] / n + kEps);
+  const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;
+  const float coef_ss = -0.5f * __ldg(g_ssim + sc.b) * inv_div / (3.0f * n);
+
+  float mom[3][2][5], abc[3][2][3], xy[3][2][2], wl1[3][2][2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) mom[a][k][j] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) abc[a][k][j] = 0.0f;
+      xy[a][k][0] = xy[a][k][1] = wl1[a][k][0] = wl1[a][k][1] = 0.0f;
+    }
+
+  const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
+  float2 pre[3][3];       // three rows in flight: (I, W, w) pairs
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int r = r_begin + u;
+    const bool inb = pin && r >= 0 && r < H && r <= r_end;
+    const unsigned o = (unsigned)max(r, 0) * W;
+    const float2 z = make_float2(0.f, 0.f);
+    pre[u][0] = inb ? __ldg(reinterpret_cast<const float2*>(img + o)) : z;
+    pre[u][1] = inb ? __ldg(reinterpret_cast<const float2*>(wrp + o)) : z;
+    pre[u][2] = inb ? __ldg(reinterpret_cast<const float2*>(wgt + o)) : z;
+  }
+  for (int rb = r_begin; rb <= r_end; rb += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int r = rb + u;
+      if (r > r_end) break;
+      // ring slots: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
+      const float2 vI = pre[u][0], vW = pre[u][1], vw = pre[u][2];
+      {
+        const int rn = r + 3;
+        const bool inb = pin && rn < H && rn <= r_end;     // rn >= 1 here
+        const unsigned o = (unsigned)min(rn, H - 1) * W;
+        const float2 z = make_float2(0.f, 0.f);
+        pre[u][0] = inb ? __ldg(reinterpret_cast<const float2*>(img + o)) : z;
+        pre[u][1] = inb ? __ldg(reinterpret_cast<const float2*>(wrp + o)) : z;
+        pre[u][2] = inb ? __ldg(reinterpret_cast<const float2*>(wgt + o)) : z;
+      }
+      const float d0 = vI.x - vW.x, d1 = vI.y - vW.y;
+      wl1[u][0][0] = vw.x;
+      wl1[u][1][0] = vw.y;
+      wl1[u][0][1] = (d0 > 0.0f ? -coef_l1 : (d0 < 0.0f ? coef_l1 : 0.0f)) * vw.x;   // d(masked L1)/dW = -sign(I-W) w coef
+      wl1[u][1][1] = (d1 > 0.0f ? -coef_l1 : (d1 < 0.0f ? coef_l1 : 0.0f)) * vw.y;
+      xy[u][0][0] = vI.x * vw.x; xy[u][0][1] = vW.x * vw.x;
+      xy[u][1][0] = vI.y * vw.y; xy[u][1][1] = vW.y * vw.y;
+      pair_moments(xy[u][0][0], xy[u][0][1], xy[u][1][0], xy[u][1][1], mom[u][0], mom[u][1]);
+
+      const int q = r - 1;
+      if (q >= sc.y0 - 1) {
+        const bool q_in = pin && q >= 0 && q < H;
+        float c0[3], c1[3];
+        ssim_coeffs(mom[0][0], mom[1][0], mom[2][0], q_in, coef_ss, c0);
+        ssim_coeffs(mom[0][1], mom[1][1], mom[2][1], q_in, coef_ss, c1);
+        float* dst0 = abc[(u + 2) % 3][0];
+        float* dst1 = abc[(u + 2) % 3][1];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float lft = __shfl_up_sync(kFullMask, c1[j], 1), rgt = __shfl_down_sync(kFullMask, c0[j], 1);
+          const float mid = c0[j] + c1[j];
+          dst0[j] = mid + lft;
+          dst1[j] = mid + rgt;
+        }
+      }
+
+      const int p = r - 2;
+      if (p >= sc.y0 && p < sc.y1 && pout) {
+        const int sp = (u + 1) % 3;
+        float g[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float A = abc[0][k][0] + abc[1][k][0] + abc[2][k][0];
+          const float Bq = abc[0][k][1] + abc[1][k][1] + abc[2][k][1];
+          const float Cq = abc[0][k][2] + abc[1][k][2] + abc[2][k][2];
+          const float gy = fmaf(xy[sp][k][0], Cq, fmaf(2.0f * xy[sp][k][1], Bq, A));
+          g[k] = fmaf(gy, wl1[sp][k][0], wl1[sp][k][1]);
+        }
+        *reinterpret_cast<float2*>(gout + (unsigned)p * W) = make_float2(g[0], g[1]);
+      }
+    }
+  }
+}
+
 int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm,
-                bool split = false) {
+                bool split = false, int ppl = 1) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "photo_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0, "photo_loss: bad batch %d", B);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -439,7 +583,8 @@ int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int 
     W[l] = L.W;
   }
   // split backward: one block per strip; fused backward: two grid rows (directions) of 4-warp blocks
-  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, (bwd && !split) ? 2 : 1, blocks_per_sm, split ? 1 : kWarpsPerBlock) > 0,
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, (bwd && !split) ? 2 : 1, blocks_per_sm,
+                                split ? 1 : kWarpsPerBlock, ppl) > 0,
               "photo_loss: problem too large");
   return UOF_OK;
 }
@@ -470,6 +615,23 @@ extern "C" int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, in
   PhotoParams P;
   bool have_weights = levels != nullptr && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS;
   for (int l = 0; have_weights && l < nlevels; ++l) have_weights = levels[l].weight_l && levels[l].weight_r;
+  bool even_w = have_weights;
+  for (int l = 0; even_w && l < nlevels; ++l) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(levels[l].img) | reinterpret_cast<uintptr_t>(levels[l].warped_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].warped_r) | reinterpret_cast<uintptr_t>(levels[l].weight_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].weight_r) | reinterpret_cast<uintptr_t>(levels[l].gwarped_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].gwarped_r);
+    even_w = (levels[l].W % 2 == 0) && (bits & 7u) == 0;
+  }
+  static const bool no_pair = getenv("UOF_PHOTO_NO_PAIR") != nullptr;
+  if (even_w && !no_pair) {     // two pixels per lane, float2 accesses
+    static const int occ_pair = resident_blocks(photo_loss_bwd_pair_kernel, kSplitWarps * 32);
+    if (int rc = fill_params(P, levels, nlevels, B, 2, true, occ_pair, /*split=*/true, /*ppl=*/2)) return rc;
+    photo_loss_bwd_pair_kernel<<<P.T.warp_begin[nlevels], kSplitWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+        P, sums, g_loss_pixel, g_loss_ssim);
+    count_launch();
+    return check_launch("photo_loss_bwd (pair)");
+  }
   if (have_weights) {     // weight maps of the forward pass are available: (strip, direction, channel) warps
     static const int occ_split = resident_blocks(photo_loss_bwd_split_kernel, kSplitWarps * 32);
     if (int rc = fill_params(P, levels, nlevels, B, 2, true, occ_split, /*split=*/true)) return rc;

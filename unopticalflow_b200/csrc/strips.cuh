@@ -18,7 +18,8 @@ struct Strip {
   int level, b, col, y0, y1;
 };
 
-template <int HALO>
+// PPL = pixels per lane: a lane owns PPL adjacent columns, s.col is its first one.
+template <int HALO, int PPL = 1>
 __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int lane, Strip& s) {
   if (gw >= T.warp_begin[T.nlevels]) return false;
   int l = 0;
@@ -28,7 +29,7 @@ __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int la
   const int sy = (local / T.strips_x[l]) % T.strips_y[l];
   s.level = l;
   s.b = local / (T.strips_x[l] * T.strips_y[l]);
-  s.col = sx * (32 - 2 * HALO) - HALO + lane;
+  s.col = sx * (32 * PPL - 2 * HALO) - HALO + lane * PPL;
   s.y0 = sy * T.rows;
   s.y1 = min(s.y0 + T.rows, T.H[l]);
   return true;
@@ -39,10 +40,10 @@ __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int la
 // height is the one that minimises (number of waves) x (rows + 2*halo), i.e. whole waves with the least halo
 // re-computation (a 1.3-wave launch costs as much as a 2-wave one).  Returns the number of warps, or -1 on overflow.
 inline long long build_strip_table(StripTable& T, const int* H, const int* W, int nlevels, int B, int halo,
-                                   int grid_mult = 1, int blocks_per_sm = 4, int warps_per_block = 4) {
+                                   int grid_mult = 1, int blocks_per_sm = 4, int warps_per_block = 4, int ppl = 1) {
   T.nlevels = nlevels;
   T.B = B;
-  const int outw = 32 - 2 * halo;
+  const int outw = 32 * ppl - 2 * halo;
   const long long slots = (long long)kNumSMs * (blocks_per_sm > 0 ? blocks_per_sm : 1);
   int best_rows = 8;
   double best_cost = 1e300;

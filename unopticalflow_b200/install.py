@@ -34,6 +34,14 @@ def _consis(self, fwd_flow_pyramid, bwd_flow_pyramid, occ_mask_list):
     return ops.flow_consis_loss(fwd_flow_pyramid, bwd_flow_pyramid, occ_mask_list, self.num_scales)
 
 
+def _diff_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
+    return ops.diff_weight(img_pyramid_from_l, img_pyramid, img_pyramid_from_r, self.num_scales)
+
+
+def _loss_with_mask(self, diff_list, occ_mask_list):
+    return ops.loss_with_mask(diff_list, occ_mask_list, self.num_scales)
+
+
 def _pyramid(self, img, num_pyramid):
     return ops.img_pyramid(img, num_pyramid)
 
@@ -64,8 +72,11 @@ def install(modules=None, models=()):
         cls.compute_loss_flow_consis = _consis
         cls.generate_img_pyramid = _pyramid
         cls.warp_flow_pyramid = _warp_pyramid
+        cls.compute_diff_weight = _diff_weight
+        cls.compute_loss_with_mask = _loss_with_mask
         done += [('model_flow_paper', 'Model_flow.' + n) for n in
-                 ('compute_loss_flow_smooth', 'compute_loss_flow_consis', 'generate_img_pyramid', 'warp_flow_pyramid')]
+                 ('compute_loss_flow_smooth', 'compute_loss_flow_consis', 'generate_img_pyramid', 'warp_flow_pyramid',
+                  'compute_diff_weight', 'compute_loss_with_mask')]
     for model in models:                                 # instances built before install()
         inner = getattr(model, 'module', model)
         if hasattr(inner, 'pwc_model'):

@@ -48,22 +48,12 @@ class Model_flow(nn.Module):
                 for i, f in zip(img_pyramid, flow_pyramid)]
 
     def compute_diff_weight(self, img_pyramid_from_l, img_pyramid, img_pyramid_from_r):
-        """-> diff_bwd, diff_fwd, weight_bwd, weight_fwd (model_flow_paper.py:101-134).  Weights come from
-        the fused kernel (detached, as in the reference); the differentiable diff maps are plain tensor ops."""
-        S = self.num_scales
-        _, _, w_b, w_f = ops.photometric_losses([t.detach() for t in img_pyramid[:S]],
-                                                [t.detach() for t in img_pyramid_from_l[:S]],
-                                                [t.detach() for t in img_pyramid_from_r[:S]], S)
-        d_b = [(img_pyramid[s] - img_pyramid_from_l[s]).abs().mean(1, True) for s in range(S)]
-        d_f = [(img_pyramid[s] - img_pyramid_from_r[s]).abs().mean(1, True) for s in range(S)]
-        return d_b, d_f, w_b, w_f
+        """-> diff_bwd, diff_fwd, weight_bwd, weight_fwd (model_flow_paper.py:101-134); weights detached as in the
+        reference, diffs differentiable w.r.t. the warped images."""
+        return ops.diff_weight(img_pyramid_from_l, img_pyramid, img_pyramid_from_r, self.num_scales)
 
     def compute_loss_with_mask(self, diff_list, occ_mask_list):
-        total = 0
-        for s in range(self.num_scales):
-            d, m = diff_list[s], occ_mask_list[s]
-            total = total + (d * m).mean((1, 2, 3)) / (m.mean((1, 2, 3)) + 1e-12)
-        return total
+        return ops.loss_with_mask(diff_list, occ_mask_list, self.num_scales)
 
     def compute_loss_ssim(self, img_pyramid, img_warped_pyramid, occ_mask_list):
         total = 0

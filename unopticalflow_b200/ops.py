@@ -254,6 +254,87 @@ def photometric_losses_stacked(img_pyramid, warped_lr, num_scales=3, return_diff
     return _unpack_photo(outs, S, return_diffs)
 
 
+# ------------------------------------------------------------------------------- a4 / a5 seams
+class _DiffWeight(torch.autograd.Function):
+    """One level of compute_diff_weight: -> diff_l, diff_r (differentiable), weight_l, weight_r (detached)."""
+
+    @staticmethod
+    def forward(ctx, img, wl, wr):
+        img, wl, wr = img.contiguous(), wl.contiguous(), wr.contiguous()
+        B, _, H, W = img.shape
+        outs = [torch.empty((B, 1, H, W), device=img.device) for _ in range(4)]
+        with torch.cuda.device_of(img):
+            _lib.call('uof_diff_weight_fwd', _p(img), _p(wl), _p(wr), *[_p(t) for t in outs], B, H, W, _stream(img))
+        ctx.save_for_backward(img, wl, wr)
+        ctx.mark_non_differentiable(outs[2], outs[3])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_dl, g_dr, *unused):
+        img, wl, wr = ctx.saved_tensors
+        B, _, H, W = img.shape
+        gl, gr = torch.empty_like(wl), torch.empty_like(wr)
+        g_dl = None if g_dl is None else g_dl.contiguous()
+        g_dr = None if g_dr is None else g_dr.contiguous()
+        with torch.cuda.device_of(img):
+            _lib.call('uof_diff_weight_bwd', _p(img), _p(wl), _p(wr), _p(g_dl), _p(g_dr), _p(gl), _p(gr), B, H, W, _stream(img))
+        return None, gl, gr
+
+
+def diff_weight(img_from_l, img, img_from_r, num_scales=3):
+    """Drop-in for Model_flow.compute_diff_weight (model_flow_paper.py:101-134):
+    -> diff_bwd, diff_fwd, weight_bwd, weight_fwd ("bwd" <-> left image, "fwd" <-> right image)."""
+    d_b, d_f, w_b, w_f = [], [], [], []
+    for s in range(num_scales):
+        _require_cuda(img[s], img_from_l[s], img_from_r[s])
+        assert img[s].shape[1] == 3 and img_from_l[s].shape == img[s].shape == img_from_r[s].shape
+        dl, dr, wl, wr = _DiffWeight.apply(img[s].detach(), img_from_l[s], img_from_r[s])
+        d_b.append(dl); d_f.append(dr); w_b.append(wl); w_f.append(wr)
+    return d_b, d_f, w_b, w_f
+
+
+class _MaskedMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S, *tensors):
+        diffs = [t.contiguous() for t in tensors[:S]]
+        masks = [t.contiguous() for t in tensors[S:2 * S]]
+        B, C = diffs[0].shape[0], diffs[0].shape[1]
+        dev = diffs[0].device
+        for d, m in zip(diffs, masks):
+            assert d.shape[1] == C and m.shape[1] == 1 and d.shape[2:] == m.shape[2:] and d.shape[0] == m.shape[0] == B
+        arr = lambda ts: (ctypes.c_void_p * S)(*[t.data_ptr() for t in ts])
+        Hs = (ctypes.c_int * S)(*[d.shape[2] for d in diffs])
+        Ws = (ctypes.c_int * S)(*[d.shape[3] for d in diffs])
+        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        with torch.cuda.device_of(diffs[0]):
+            _lib.call('uof_masked_mean_fwd', arr(diffs), arr(masks), Hs, Ws, S, B, C, _p(sums), _p(loss), _stream(diffs[0]))
+        ctx.save_for_backward(sums, *diffs, *masks)
+        ctx.S = S
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        S = ctx.S
+        sums, *rest = ctx.saved_tensors
+        diffs, masks = rest[:S], rest[S:]
+        B, C = diffs[0].shape[0], diffs[0].shape[1]
+        gd = [torch.empty_like(d) for d in diffs]
+        arr = lambda ts: (ctypes.c_void_p * S)(*[t.data_ptr() for t in ts])
+        Hs = (ctypes.c_int * S)(*[d.shape[2] for d in diffs])
+        Ws = (ctypes.c_int * S)(*[d.shape[3] for d in diffs])
+        g = g.contiguous()
+        with torch.cuda.device_of(g):
+            _lib.call('uof_masked_mean_bwd', arr(diffs), arr(masks), arr(gd), Hs, Ws, S, B, C, _p(sums), _p(g), _stream(g))
+        return (None, *gd, *([None] * S))
+
+
+def loss_with_mask(diff_list, occ_mask_list, num_scales=3):
+    """Drop-in for Model_flow.compute_loss_with_mask (model_flow_paper.py:90-99); the mask carries no gradient."""
+    S = num_scales
+    _require_cuda(*diff_list[:S], *occ_mask_list[:S])
+    return _MaskedMean.apply(S, *diff_list[:S], *[m.detach() for m in occ_mask_list[:S]])
+
+
 # ------------------------------------------------------------------------------------------ a7
 class _SmoothLoss(torch.autograd.Function):
     @staticmethod
