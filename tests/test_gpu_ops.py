@@ -59,6 +59,25 @@ def test_cost_volume_golden(U):
         assert_close(g2, g['g2'], REL_TOL)
 
 
+@pytest.mark.parametrize('shape', [(2, 32, 16, 24), (2, 5, 7, 9), (1, 64, 32, 104)])
+def test_corr_concat_matches_cat(U, shape):
+    """Decoder glue fusion: cat((corr, c1, up), 1) with the cost volume written in place, values and grads."""
+    g = torch.Generator().manual_seed(sum(shape))
+    B, C, H, W = shape
+    c1 = torch.randn(shape, generator=g, requires_grad=True)
+    c2 = torch.randn(shape, generator=g, requires_grad=True)
+    up = torch.randn(B, 2, H, W, generator=g, requires_grad=True)
+    ct = torch.randn(B, 81 + C + 2, H, W, generator=g)
+    ref = torch.cat((O.cost_volume(c1, c2), c1, up), 1)
+    rg = torch.autograd.grad((ref * ct).sum(), (c1, c2, up))
+    a, b, u_ = gpu(c1, True), gpu(c2, True), gpu(up, True)
+    out = U.ops.corr_concat(a, b, u_)
+    gg = torch.autograd.grad((out * ct.cuda()).sum(), (a, b, u_))
+    assert_close(out, ref, REL_TOL)
+    for x_, y_ in zip(gg, rg):
+        assert_close(x_, y_, REL_TOL)
+
+
 def test_cost_volume_full_size_properties(U):
     """B=8 level-2 shape of the 256x832 config: centre displacement == channel mean of products,
     shifted displacement == shifted product, linearity, and <gout, corr(f1,f2)> == <gf1, f1> (Euler)."""

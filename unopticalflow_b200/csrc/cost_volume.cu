@@ -281,7 +281,7 @@ extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
   if (cv::fwd_tma(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);
-  const int ksplit = cv::pick_split((long long)tx * ty * B, nchunks);
+  const int ksplit = cv::pick_ksplit_atomic((long long)tx * ty * B, nchunks);
   UOF_REQUIRE((long long)B * ksplit <= 65535, "cost_volume_fwd: batch too large for one launch");
   if (ksplit > 1) {
     UOF_CUDA(cudaMemset2DAsync(out, out_batch_stride * sizeof(float), 0,

@@ -20,6 +20,15 @@ inline int pick_split(long long ctas, int nchunks) {
   return s;
 }
 
+// Forward split-K goes through fp32 atomics into a zeroed output, which is expensive (measured: the 32x104 level takes
+// 25 us unsplit vs 47 us split in two, profiles/r1_cv_ksplit_sweep.txt): split only when there are fewer tiles than
+// ~SMs, and only up to ~120 CTAs.
+inline int pick_ksplit_atomic(long long ctas, int nchunks) {
+  int s = (int)((120 + ctas - 1) / ctas);
+  if (s < 1) s = 1;
+  return s < nchunks ? s : nchunks;
+}
+
 // TMA + mbarrier implementations.  Return false when the TMA path does not apply (W % 4 != 0, unaligned
 // pointers, no driver entry point, UOF_DISABLE_TMA=1); otherwise launch and store the status in *rc.
 bool fwd_tma(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,

@@ -315,7 +315,11 @@ int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H
   if (!make_nchw_map(&m1, f1, B, C, H, W, T::TW, T::TH, CK) || !make_nchw_map(&m2, f2, B, C, H, W, T::HTW, T::HTH, CK))
     return -1;
   const int tx = ceil_div(W, T::TW), ty = ceil_div(H, T::TH);
-  const int ksplit = pick_split((long long)tx * ty * B, ceil_div(C, CK));
+  int ksplit = pick_ksplit_atomic((long long)tx * ty * B, ceil_div(C, CK));
+  {
+    static const char* force = getenv("UOF_CV_KSPLIT");
+    if (force) ksplit = max(1, min(atoi(force), ceil_div(C, CK)));
+  }
   UOF_REQUIRE((long long)B * ksplit <= 65535 && ty <= 65535, "cost_volume_fwd: grid too large");
   if (ksplit > 1)
     UOF_CUDA(cudaMemset2DAsync(out, out_bs * sizeof(float), 0, (size_t)UOF_NUM_DISPLACEMENTS * H * W * sizeof(float), B, stream));

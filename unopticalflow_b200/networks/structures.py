@@ -91,8 +91,11 @@ class PWC_tf(nn.Module):
             if up is None:
                 flow, x4 = self._level(lvl, self.corr(c1, c2))
             else:
-                cv = self.corr(c1, self.warp(c2, up))
-                res, x4 = self._level(lvl, torch.cat((cv, c1, up), 1))
+                if self.corr == self.corr_cuda:      # default seam: cost volume written straight into the concat buffer
+                    x = ops.corr_concat(c1, self.warp(c2, up), up)
+                else:                                # a user-installed corr keeps the reference's three-step form
+                    x = torch.cat((self.corr(c1, self.warp(c2, up)), c1, up), 1)
+                res, x4 = self._level(lvl, x)
                 flow = res + up
             flows[lvl] = flow
             if lvl > 2:

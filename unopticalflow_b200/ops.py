@@ -71,6 +71,45 @@ def corr(input1: torch.Tensor, input2: torch.Tensor) -> torch.Tensor:
     return _CostVolume.apply(input1, input2)
 
 
+class _CostVolumeConcat(torch.autograd.Function):
+    """cat((corr(c1, c2w), c1, up_flow), 1) with the cost volume written straight into the concat buffer (forward) and
+    its gradient read in place from the buffer's gradient (backward): SURVEY 8(f) "decoder glue fusion".  Saves the copy of
+    the (B,81,h,w) cost volume into the concat on the way forward and the .contiguous() of its gradient slice on the way
+    back (pwc_tf.py:122-123 and the matching lines of every decoder level)."""
+
+    @staticmethod
+    def forward(ctx, c1, c2w, up_flow):
+        c1c, c2c = c1.contiguous(), c2w.contiguous()
+        B, C, H, W = c1c.shape
+        ctot = NUM_DISPLACEMENTS + C + 2
+        x = torch.empty((B, ctot, H, W), device=c1.device, dtype=torch.float32)
+        with torch.cuda.device_of(c1c):
+            _lib.call('uof_cost_volume_fwd', _p(c1c), _p(c2c), _p(x), B, C, H, W, ctot * H * W, _stream(c1c))
+        x[:, NUM_DISPLACEMENTS:NUM_DISPLACEMENTS + C].copy_(c1c)
+        x[:, NUM_DISPLACEMENTS + C:].copy_(up_flow)
+        ctx.save_for_backward(c1c, c2c)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        c1c, c2c = ctx.saved_tensors
+        B, C, H, W = c1c.shape
+        ctot = NUM_DISPLACEMENTS + C + 2
+        gx = gx.contiguous()
+        g1, g2 = torch.empty_like(c1c), torch.empty_like(c2c)
+        with torch.cuda.device_of(c1c):
+            _lib.call('uof_cost_volume_bwd', _p(gx), ctot * H * W, _p(c1c), _p(c2c), _p(g1), _p(g2), B, C, H, W, _stream(c1c))
+        g1 += gx[:, NUM_DISPLACEMENTS:NUM_DISPLACEMENTS + C]
+        return g1, g2, gx[:, NUM_DISPLACEMENTS + C:]
+
+
+def corr_concat(c1: torch.Tensor, c2_warped: torch.Tensor, up_flow: torch.Tensor) -> torch.Tensor:
+    """== torch.cat((corr(c1, c2_warped), c1, up_flow), 1) (pwc_tf.py:122-123), fused."""
+    assert c1.shape == c2_warped.shape and up_flow.shape[1] == 2 and up_flow.shape[2:] == c1.shape[2:]
+    _require_cuda(c1, c2_warped, up_flow)
+    return _CostVolumeConcat.apply(c1, c2_warped, up_flow)
+
+
 # --------------------------------------------------------------------------------------- a2/a3
 def _is_channels_last(x):
     return (x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] > 1 and not x.is_contiguous()
