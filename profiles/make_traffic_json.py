@@ -45,7 +45,7 @@ def main(launch_csv, calls_json, out_path):
     table = {}
     for i in order:
         r = recs[i]
-        if 'uof' not in r['name'] or 'finalize' in r['name']:
+        if 'finalize' in r['name']:
             continue
         fn = re.sub(r'[<(].*', '', r['name'].replace('<unnamed>', 'anon')).split('::')[-1].strip()
         entry = next((e for k, e in MAIN.items() if fn.startswith(k)), None)

@@ -6,6 +6,10 @@ import sys
 from collections import defaultdict
 
 
+OWN = re.compile(r'cost_volume_|warp_(fwd|bwd)_n|photo_loss_|smooth_(fwd|bwd|finalize)|consis_(fwd|bwd|finalize)|pyramid_|ssim_(fwd|bwd)_kernel|'
+                 r'splat|fb_mask|clamp01|diff_weight_|masked_mean_')
+
+
 def main(path):
     with open(path) as f:
         lines = [l for l in f if not l.startswith('==')]
@@ -30,10 +34,10 @@ def main(path):
         r = recs[k]
         t = r.get('gpu__time_duration.sum', 0.0)
         tot += t
-        if 'uof' not in r['name']:
+        if not OWN.search(r['name']):
             continue
         own += t
-        nm = re.sub(r'\(.*', '', r['name']).replace('void ', '').replace('uof::<unnamed>::', '')
+        nm = re.sub(r'\(.*', '', r['name']).replace('void ', '').replace('uof::', '').replace('cv::', '').replace('<unnamed>::', '')
         print('%-34s %-16s %9.1f %10.0f %9.2f %9.2f' % (nm[:34], r['grid'], t, r.get('smsp__inst_executed.sum', 0),
                                                           r.get('dram__bytes_read.sum', 0), r.get('dram__bytes_write.sum', 0)))
     print('own kernels %.1f us of %.1f us total (%.2f %%), %d launches in the step' % (own, tot, 100 * own / tot, len(order)))
