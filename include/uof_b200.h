@@ -156,6 +156,14 @@ int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, 
                     long long stride_h, float* const* outs /* host array of nlevels-1 device pointers */,
                     int nlevels, int nimg, int B, int C, int H, int W, uof_stream_t stream);
 
+/* a11 glue: fused bias + LeakyReLU after a bias-free convolution.  Replaces the bias epilogue + LeakyReLU
+ * of conv() (net_utils.py:7-11) forward, and LeakyReLU-backward + bias-gradient reduction backward.
+ * y: (B,C,H,W) convolution output, updated IN PLACE to lrelu(y + bias[c]). */
+int uof_bias_lrelu_fwd(float* y, const float* bias, int B, int C, int H, int W, float slope, uof_stream_t stream);
+/* y = the post-activation tensor of the forward pass; gx (B,C,H,W) overwritten, gbias (C) zero-filled then accumulated. */
+int uof_bias_lrelu_bwd(const float* gout, const float* y, float* gx, float* gbias, int B, int C, int H, int W,
+                       float slope, uof_stream_t stream);
+
 /* a12: forward splat ("transformerFwd").  NOT in the reference.
  * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;
  * out: (B,H,W,C), zero-filled here then accumulated with warp-aggregated fp32 atomics. */

@@ -59,6 +59,28 @@ def test_cost_volume_golden(U):
         assert_close(g2, g['g2'], REL_TOL)
 
 
+@pytest.mark.parametrize('cin,cout,h,w,stride,dil', [(3, 16, 64, 96, 2, 1), (32, 24, 13, 7, 1, 1), (8, 8, 20, 26, 1, 4)])
+def test_conv_block_fused_bias_lrelu(U, cin, cout, h, w, stride, dil):
+    """conv() block = bias-free cuDNN conv + fused bias+LeakyReLU kernel: same values and gradients (input, weight, bias)
+    as the reference's nn.Sequential(Conv2d, LeakyReLU(0.1)) (net_utils.py:7-11) on the same GPU."""
+    import torch.nn as nn
+    from unopticalflow_b200.networks.structures import conv
+    torch.manual_seed(3)
+    blk = conv(cin, cout, stride=stride, padding=dil, dilation=dil).cuda()
+    ref = nn.Sequential(nn.Conv2d(cin, cout, 3, stride, dil, dil), nn.LeakyReLU(0.1)).cuda()
+    ref.load_state_dict(blk.state_dict())
+    assert list(blk.state_dict().keys()) == ['0.weight', '0.bias']
+    x = torch.randn(3, cin, h, w, device='cuda')
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = blk(xa), ref(xb)
+    ct = torch.randn_like(yb)
+    ga = torch.autograd.grad((ya * ct).sum(), [xa, blk[0].weight, blk[0].bias])
+    gb = torch.autograd.grad((yb * ct).sum(), [xb, ref[0].weight, ref[0].bias])
+    assert_close(ya, yb, 1e-6, 'conv block fwd')
+    for a, b, what in zip(ga, gb, ('input', 'weight', 'bias')):
+        assert_close(a, b, 1e-5, 'conv block grad ' + what)
+
+
 @pytest.mark.parametrize('shape', [(2, 32, 16, 24), (2, 5, 7, 9), (1, 64, 32, 104)])
 def test_corr_concat_matches_cat(U, shape):
     """Decoder glue fusion: cat((corr, c1, up), 1) with the cost volume written in place, values and grads."""

@@ -21,10 +21,22 @@ _LEVEL_C = {6: 196, 5: 128, 4: 96, 3: 64, 2: 32}
 _CONTEXT = ((128, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1))
 
 
+class ConvLReLU(nn.Sequential):
+    """nn.Sequential(Conv2d(bias=True), LeakyReLU(0.1)) -- the reference's `conv()` block (net_utils.py:7-11), same
+    modules and state-dict keys ('0.weight', '0.bias') -- executed as a bias-free cuDNN convolution followed by ONE fused
+    bias + LeakyReLU kernel (in place), whose backward also produces the bias gradient.  Like every other operator of
+    the package it has no CPU path."""
+
+    def forward(self, x):
+        cv, act = self[0], self[1]
+        y = F.conv2d(x, cv.weight, None, cv.stride, cv.padding, cv.dilation, cv.groups)
+        return ops.bias_leaky_relu_(y, cv.bias, act.negative_slope)
+
+
 def conv(in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1):
     """Conv2d + LeakyReLU(0.1) (net_utils.py:7-11)."""
-    return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=padding,
-                                   dilation=dilation, bias=True), nn.LeakyReLU(0.1))
+    return ConvLReLU(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=padding,
+                               dilation=dilation, bias=True), nn.LeakyReLU(0.1))
 
 
 class FeaturePyramid(nn.Module):

@@ -464,6 +464,42 @@ def flow_consis_loss(fwd_flows, bwd_flows, weights_fwd, num_scales=3):
                              *[t.detach() for t in weights_fwd[:S]])
 
 
+# ------------------------------------------------------------------------------------ a11 glue
+class _BiasLeakyReLU(torch.autograd.Function):
+    """y <- lrelu(y + bias[c]) in place on a fresh convolution output; backward fuses LeakyReLU-backward with the bias
+    gradient reduction (glue around the kept-PyTorch convolutions, net_utils.py:7-11)."""
+
+    @staticmethod
+    def forward(ctx, y, bias, slope):
+        assert y.is_contiguous()
+        B, C, H, W = y.shape
+        with torch.cuda.device_of(y):
+            _lib.call('uof_bias_lrelu_fwd', _p(y), _p(bias), B, C, H, W, float(slope), _stream(y))
+        ctx.mark_dirty(y)
+        ctx.save_for_backward(y)
+        ctx.slope = float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gout):
+        (y,) = ctx.saved_tensors
+        B, C, H, W = y.shape
+        gout = gout.contiguous()
+        gx = torch.empty_like(y)
+        gbias = torch.empty(C, device=y.device, dtype=torch.float32)
+        with torch.cuda.device_of(y):
+            _lib.call('uof_bias_lrelu_bwd', _p(gout), _p(y), _p(gx), _p(gbias), B, C, H, W, ctx.slope, _stream(y))
+        return gx, gbias, None
+
+
+def bias_leaky_relu_(y: torch.Tensor, bias: torch.Tensor, negative_slope: float = 0.1) -> torch.Tensor:
+    """In-place lrelu(y + bias[None,:,None,None]); `y` must be a freshly produced (non-leaf) contiguous NCHW tensor."""
+    _require_cuda(y, bias)
+    if not y.is_contiguous():
+        y = y.contiguous()
+    return _BiasLeakyReLU.apply(y, bias.contiguous(), negative_slope)
+
+
 # ------------------------------------------------------------------------------------------ a9
 def _pyramid_launch(base, nimg, stride_img, B, C, H, W, sb, sc, sh, num_pyramid):
     lv = [torch.empty((nimg, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=base.device) for s in range(1, num_pyramid)]
