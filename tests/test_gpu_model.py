@@ -103,6 +103,25 @@ def test_train_steps_track_oracle(U):
         assert abs(float(lg) - float(lr)) <= 2e-4 * abs(float(lr)), (step, float(lg), float(lr))
 
 
+def test_graphed_train_step_matches_eager(U):
+    """The CUDA-graph replay of the whole iteration (train.GraphedTrainStep) follows the eager trajectory."""
+    from unopticalflow_b200 import train as T
+    torch.manual_seed(0)
+    m1, m2 = U.Model_flow(T.KITTI_CFG).cuda(), U.Model_flow(T.KITTI_CFG).cuda()
+    m2.load_state_dict(m1.state_dict())
+    w = T.generate_loss_weights_dict(T.KITTI_CFG)
+    gen = torch.Generator().manual_seed(1234)
+    xs = [torch.rand(2, 3, 192, 128, generator=gen).cuda() for _ in range(3)]
+    opt = T.make_optimizer(m1)
+    graphed = T.GraphedTrainStep(m2, xs[0], w, warmup=3)          # three real warm-up steps on xs[0]; capture does not execute
+    for _ in range(3):
+        T.train_step(m1, opt, xs[0], w)
+    for i in range(4):
+        le = float(T.train_step(m1, opt, xs[i % 3], w))
+        lg = float(graphed(xs[i % 3]))
+        assert abs(le - lg) <= 2e-4 * abs(le), (i, le, lg)
+
+
 def test_occlusion_extras(U):
     _, m = build_pair(U)
     f = torch.randn(2, 2, 32, 48, device='cuda') * 2

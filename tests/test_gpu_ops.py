@@ -279,6 +279,44 @@ def test_photometric_fused_vs_oracle(U, B, H, W):
         assert_close(g2[s], torch.cat((got_g[s], got_g[S + s]), 0), 1e-5)
 
 
+def test_photometric_backward_kernel_variants_agree(U):
+    """uof_photo_loss_bwd has three kernels: pixel-pair (weights given, even W), split (weights given, odd W somewhere)
+    and fused-direction (no weight maps: recomputes them).  All must produce the same gradients through the C ABI."""
+    import ctypes
+    from unopticalflow_b200 import _lib
+    from unopticalflow_b200._lib import PhotoLevel
+    g = torch.Generator().manual_seed(77)
+    B, S = 2, 2
+    for (H, W) in ((24, 40), (24, 38)):            # 40/20 even -> pair kernel;  38/19 -> split kernel
+        imgs = [torch.rand(B, 3, H >> s, W >> s, generator=g).cuda() for s in range(S)]
+        wl = [(torch.rand(B, 3, H >> s, W >> s, generator=g) * (torch.rand(B, 1, H >> s, W >> s, generator=g) > 0.1)).cuda()
+              for s in range(S)]
+        wr = [torch.rand(B, 3, H >> s, W >> s, generator=g).cuda() for s in range(S)]
+        wtl = [torch.empty(B, 1, H >> s, W >> s, device='cuda') for s in range(S)]
+        wtr = [torch.empty(B, 1, H >> s, W >> s, device='cuda') for s in range(S)]
+        sums, lp, ls = torch.empty(S, B, 6, device='cuda'), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+        gp, gs = torch.rand(B, generator=g).cuda(), torch.rand(B, generator=g).cuda()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+
+        def levels(with_weights, gl, gr):
+            lv = (PhotoLevel * S)()
+            for s in range(S):
+                lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(),
+                                   wtl[s].data_ptr() if with_weights else None, wtr[s].data_ptr() if with_weights else None,
+                                   None, None, gl[s].data_ptr(), gr[s].data_ptr(), H >> s, W >> s)
+            return lv
+        dummy = [torch.empty_like(t) for t in wl]
+        _lib.call('uof_photo_loss_fwd', levels(True, dummy, dummy), S, B, p(sums), p(lp), p(ls), st)
+        ga_l, ga_r = [torch.zeros_like(t) for t in wl], [torch.zeros_like(t) for t in wr]
+        gb_l, gb_r = [torch.zeros_like(t) for t in wl], [torch.zeros_like(t) for t in wr]
+        _lib.call('uof_photo_loss_bwd', levels(True, ga_l, ga_r), S, B, p(sums), p(gp), p(gs), st)      # pair or split
+        _lib.call('uof_photo_loss_bwd', levels(False, gb_l, gb_r), S, B, p(sums), p(gp), p(gs), st)     # fused-direction
+        for a, b in zip(ga_l + ga_r, gb_l + gb_r):
+            assert float(b.abs().max()) > 0
+            assert_close(a, b, 1e-5, 'photo bwd variants (W=%d)' % W)
+
+
 # --------------------------------------------------------------------------------------- a7/a8
 @pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 24, 66), (2, 8, 12)])
 def test_smooth_and_consis_vs_oracle(U, B, H, W):
