@@ -129,6 +129,7 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
   Footprint fp[PXT];
   float ux[PXT], uy[PXT], tx[PXT], ty[PXT], msk[PXT];
   unsigned inb[PXT];    // bit0..3: corner 00,01,10,11 in bounds
+  int x0u = 0, y0u = 0; // unclamped top-left corner (of the last pixel; only used when PXT == 1)
 #pragma unroll
   for (int k = 0; k < PXT; ++k) {
     const int px = rc.x0 + 32 * k + lane;
@@ -145,6 +146,16 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
     tx[k] = bl.tx; ty[k] = bl.ty;
     ux[k] = (floorf(ix) + 1.0f) - ix;
     uy[k] = (floorf(iy) + 1.0f) - iy;
+    x0u = bl.x0;
+    y0u = bl.y0;
+  }
+  // side-by-side test for the warp-aggregated scatter (PXT == 1 only): lane-1's footprint is one column to the left
+  bool take = false, taken = false;
+  if (NEED_GX && PXT == 1) {
+    const int px0 = __shfl_up_sync(kFullMask, x0u, 1), py0 = __shfl_up_sync(kFullMask, y0u, 1);
+    const int pok = __shfl_up_sync(kFullMask, (int)ok[0], 1);
+    take = lane > 0 && ok[0] && pok && px0 + 1 == x0u && py0 == y0u;
+    taken = __shfl_down_sync(kFullMask, (int)take, 1) && lane < 31;
   }
   const int cch = (C + nchunk - 1) / nchunk;       // channels per thread
   const int c0 = rc.chunk * cch, c1 = min(C, c0 + cch);
@@ -176,10 +187,27 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
       giy[k] = fmaf(gm, (v10 - v00) * ux[k] + (v11 - v01) * tx[k], giy[k]);
       if (NEED_GX) {
         float* q = gxp + (size_t)(c - c0) * plane;
-        if (inb[k] & 1u) atomicAdd(q + fp[k].o00, gm * fp[k].w00);
-        if (inb[k] & 2u) atomicAdd(q + fp[k].o01, gm * fp[k].w01);
-        if (inb[k] & 4u) atomicAdd(q + fp[k].o10, gm * fp[k].w10);
-        if (inb[k] & 8u) atomicAdd(q + fp[k].o11, gm * fp[k].w11);
+        float c00 = gm * fp[k].w00, c01 = gm * fp[k].w01, c10 = gm * fp[k].w10, c11 = gm * fp[k].w11;
+        if (PXT == 1) {
+          // warp-aggregated scatter: the right-hand corners of lane-1 are this lane's left-hand corners whenever the
+          // two footprints sit side by side (`take`); add them here and let lane-1 skip its two REDs (`taken`)
+          const float n01 = __shfl_up_sync(kFullMask, c01, 1), n11 = __shfl_up_sync(kFullMask, c11, 1);
+          if (take) {
+            c00 += n01;
+            c10 += n11;
+          }
+          if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
+          if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
+          if (!taken) {
+            if (inb[k] & 2u) atomicAdd(q + fp[k].o01, c01);
+            if (inb[k] & 8u) atomicAdd(q + fp[k].o11, c11);
+          }
+        } else {
+          if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
+          if (inb[k] & 2u) atomicAdd(q + fp[k].o01, c01);
+          if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
+          if (inb[k] & 8u) atomicAdd(q + fp[k].o11, c11);
+        }
       }
     }
   }

@@ -9,12 +9,14 @@ from __future__ import annotations
 
 import argparse
 import json
+import re
 
 import torch
 
 from . import _lib, ops
 
 L2_BYTES = 126e6
+FP32_PEAK_TFLOPS = 69.0      # measured on this pool's B200 with a pure FFMA kernel (profiles/microbench/ffma2_result.txt)
 LEVELS = ((196, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104), (32, 64, 208))   # (C,h,w) at 256x832, SURVEY 8
 
 
@@ -155,6 +157,20 @@ def cases(B=8, H=256, W=832):
     yield ('img_pyramid[levels 1..2 of the 3 images, one launch]', int(3 * B * 3 * H * W * 4 * (1 + 1 / 4 + 1 / 16)),
            [lambda t=t, pp=pp: _lib.call('uof_img_pyramid', ops._p(t), H * t.stride(2), t.stride(0), t.stride(1), t.stride(2), pp, S,
                                          3, B, 3, H, W, ops._stream(anchor)) for t, pp in zip(trip, pptr)])
+    # fused bias + LeakyReLU of the largest decoder activation (2B x 128 x H/4 x W/4)
+    ah, aw = H // 4, W // 4
+    ka = 3
+    acts = [r(B2, 128, ah, aw) for _ in range(ka)]
+    gacts = [r(B2, 128, ah, aw) for _ in range(ka)]
+    gxs = [torch.empty_like(a) for a in acts]
+    bias, gbias = r(128), torch.empty(128, device=dev)
+    keep.append((acts, gacts, gxs, bias, gbias))
+    nact = B2 * 128 * ah * aw
+    yield ('bias_lrelu_fwd[%dx128x%dx%d]' % (B2, ah, aw), 8 * nact,
+           [lambda a=a: _lib.call('uof_bias_lrelu_fwd', ops._p(a), ops._p(bias), B2, 128, ah, aw, 0.1, ops._stream(anchor)) for a in acts])
+    yield ('bias_lrelu_bwd[%dx128x%dx%d]' % (B2, ah, aw), 12 * nact,
+           [lambda a=a, g=g, o=o: _lib.call('uof_bias_lrelu_bwd', ops._p(g), ops._p(a), ops._p(o), ops._p(gbias), B2, 128, ah, aw, 0.1,
+                                            ops._stream(anchor)) for a, g, o in zip(acts, gacts, gxs)])
     fl_nhwc = [r(B2, H, W, 2) * 2 for _ in range(k)]
     rm = [torch.empty(B2, H, W, 1, device=dev) for _ in range(k)]
     keep.append((fl_nhwc, rm))
@@ -170,8 +186,15 @@ def run(peak_gbs, B=8, H=256, W=832, only=None):
             continue
         us = _time_graph(fns)
         gbs = nbytes / (us * 1e-6) / 1e9
-        rows.append({'kernel': name, 'avg_us': round(us, 2), 'alg_mb': round(nbytes / 1e6, 3), 'achieved_gbs': round(gbs, 1),
-                     'frac': round(gbs / peak_gbs, 4), 'buffer_sets': len(fns)})
+        row = {'kernel': name, 'avg_us': round(us, 2), 'alg_mb': round(nbytes / 1e6, 3), 'achieved_gbs': round(gbs, 1),
+               'frac': round(gbs / peak_gbs, 4), 'buffer_sets': len(fns)}
+        m = re.match(r'cost_volume_(fwd|bwd)\[(\d+)x(\d+)x(\d+)x(\d+)\]', name)
+        if m:      # the cost volume is FP32-FMA bound: also report it against the measured CUDA-core peak (SURVEY 8d FLOPs)
+            b_, c_, h_, w_ = (int(v) for v in m.groups()[1:])
+            flops = (2 if m.group(1) == 'fwd' else 4) * 81 * c_ * b_ * h_ * w_
+            row['tflops'] = round(flops / (us * 1e-6) / 1e12, 2)
+            row['fp32_frac'] = round(row['tflops'] / FP32_PEAK_TFLOPS, 3)
+        rows.append(row)
         del fns
         torch.cuda.empty_cache()
     return rows
