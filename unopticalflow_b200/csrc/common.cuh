@@ -43,6 +43,37 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Per-sample reduction epilogue of the loss kernels: every warp of the block holds K partial sums (already warp-reduced,
+// valid in lane 0) for the K consecutive floats at `dst` (nullptr: the warp had no work).  Warps that share `dst` are
+// combined through shared memory and ONE atomic per quantity is issued for the group: all warps of a launch hit the same
+// handful of addresses (one L2 slice), and ncu showed the serialised same-address REDs, not the streaming, bounding
+// consis_fwd (30 us with one RED pair per warp vs 15 us for the backward kernel moving 1.4x the bytes).
+// Must be reached by every thread of the block.
+template <int K, int WARPS>
+__device__ __forceinline__ void block_accumulate(const float (&v)[K], float* dst) {
+  __shared__ float part[WARPS][K];
+  __shared__ float* dsts[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    dsts[warp] = dst;
+#pragma unroll
+    for (int k = 0; k < K; ++k) part[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < WARPS * K) {
+    const int w = threadIdx.x / K, k = threadIdx.x - w * K;
+    float* d = dsts[w];
+    bool leader = d != nullptr;
+    for (int j = 0; j < w; ++j) leader = leader && dsts[j] != d;
+    if (leader) {
+      float s = part[w][k];
+      for (int j = w + 1; j < WARPS; ++j)
+        if (dsts[j] == d) s += part[j][k];
+      atomicAdd(d + k, s);
+    }
+  }
+}
+
 // ---- streaming loads/stores -------------------------------------------------------------------
 __device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 
@@ -51,6 +82,11 @@ __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_sr
   unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   int bytes = valid ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src, bool valid) {
+  unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src, bool valid) {
   unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));

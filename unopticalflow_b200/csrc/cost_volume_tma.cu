@@ -41,8 +41,12 @@ struct Tile {
   }
 };
 
+// Round the dynamic shared-memory base up to 128 B (TMA destination alignment) with POINTER arithmetic on the
+// __shared__ array: going through uintptr_t hid the address space from the compiler, and every window load of the
+// inner loop became a generic LD.E.128 with 64-bit address math and long-scoreboard stalls (ncu source page,
+// profiles/r2_cv_generic_ld.txt) instead of LDS.128.
 __device__ __forceinline__ float* align128(unsigned char* p) {
-  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 127) & ~static_cast<uintptr_t>(127));
+  return reinterpret_cast<float*>(p + ((128u - (smem_u32(p) & 127u)) & 127u));
 }
 
 // ------------------------------------------------------------------------------------------- forward

@@ -28,15 +28,34 @@ __device__ __forceinline__ float edge_weight(const float* a, const float* b) {
   return __expf((-10.0f / 3.0f) * (fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2])));
 }
 
-// one pixel of a row (2 flow + 3 image values), zeros outside the image
-__device__ __forceinline__ void load_row(const float* __restrict__ fb, const float* __restrict__ ib, size_t plane, int W,
-                                         int r, int H, int col, bool col_in, float* v) {
+// Row pipeline of the smoothness kernels: every warp owns a ring of kDepth rows x 5 planes x 32 lanes in shared
+// memory and keeps kDepth-1 rows in flight with cp.async (LDGSTS, 4 bytes per lane, zero-filled outside the image).
+// Register prefetching was tried first: ptxas hoists the next row's LDGs above the last use of the registers they
+// replace and then copies the just-loaded values, so each row waited for its own prefetch (long-scoreboard stalls on
+// MOVs: 39 % of the samples of smooth_fwd in the ncu source page of round 2, whatever the ring shape).  The
+// asynchronous copies take the prefetch out of the register allocator's hands and cost no registers.
+constexpr int kDepth = 4;
+constexpr int kRowVals = 5;     // flow x, flow y, image r, g, b
+
+// start the copy of row r (lane's pixel) into ring slot `slot`, one commit group per row
+__device__ __forceinline__ void fetch_row(float* ring, int slot, const float* __restrict__ fb, const float* __restrict__ ib,
+                                          size_t plane, int W, int r, int H, int colc, bool col_in) {
   const bool inb = col_in && r >= 0 && r < H;
-  const size_t off = (size_t)min(max(r, 0), H - 1) * W + max(col, 0);
-  v[0] = inb ? __ldg(fb + off) : 0.0f;
-  v[1] = inb ? __ldg(fb + off + plane) : 0.0f;
+  const size_t off = (size_t)min(max(r, 0), H - 1) * W + colc;
+  float* d = ring + slot * (kRowVals * 32);
+  cp_async_4(d, fb + off, inb);
+  cp_async_4(d + 32, fb + off + plane, inb);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) v[2 + c] = inb ? __ldg(ib + off + c * plane) : 0.0f;
+  for (int c = 0; c < 3; ++c) cp_async_4(d + (2 + c) * 32, ib + off + c * plane, inb);
+  cp_async_commit();
+}
+
+// wait for the oldest row in flight and read it
+__device__ __forceinline__ void take_row(const float* ring, int slot, float* v) {
+  cp_async_wait<kDepth - 1>();
+  const float* d = ring + slot * (kRowVals * 32);
+#pragma unroll
+  for (int k = 0; k < kRowVals; ++k) v[k] = d[k * 32];
 }
 
 // --------------------------------------------------------------------------------- smooth fwd
@@ -45,7 +64,8 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   Strip sc;
-  if (!locate_strip<1>(P.T, gw, lane, sc)) return;
+  const bool live = locate_strip<1>(P.T, gw, lane, sc);   // idle warps still join the block reduction below
+  if (!live) sc.level = sc.b = sc.col = sc.y0 = sc.y1 = 0;
   const uof_smooth_level& L = P.lv[sc.level];
   const int H = L.H, W = L.W;
   const size_t plane = (size_t)H * W;
@@ -57,10 +77,19 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
   float f[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // flow/20 at rows r-2, r-1, r
   float im[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};    // image at rows r-1, r
   float sum_x = 0.0f, sum_y = 0.0f;
+  if (live) {
 
-  float nxt[5];   // next row, prefetched one iteration ahead: flow x2, image x3
-  load_row(fb, ib, plane, W, sc.y0 - 1, H, sc.col, col_in, nxt);
+  __shared__ float ring_s[kWarpsPerBlock][kDepth * kRowVals * 32];
+  float* ring = ring_s[threadIdx.x >> 5] + lane;
+  const int colc = min(max(sc.col, 0), W - 1);
+#pragma unroll
+  for (int i = 0; i < kDepth - 1; ++i) fetch_row(ring, i, fb, ib, plane, W, sc.y0 - 1 + i, H, colc, col_in);
+  int slot = 0;
   for (int r = sc.y0 - 1; r <= sc.y1; ++r) {
+    fetch_row(ring, slot == 0 ? kDepth - 1 : slot - 1, fb, ib, plane, W, r + kDepth - 1, H, colc, col_in);
+    float nxt[kRowVals];
+    take_row(ring, slot, nxt);
+    slot = slot + 1 == kDepth ? 0 : slot + 1;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
@@ -72,7 +101,6 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
       im[0][c] = im[1][c];
       im[1][c] = nxt[2 + c];
     }
-    if (r < sc.y1) load_row(fb, ib, plane, W, r + 1, H, sc.col, col_in, nxt);
     // x term centred on (r, col): needs col-1 and col+1 from the neighbouring lanes
     float ir[3];
 #pragma unroll
@@ -91,13 +119,10 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
       sum_y = fmaf(edge_weight(im[1], im[0]), d2y, sum_y);
     }
   }
-  sum_x = warp_sum(sum_x);
-  sum_y = warp_sum(sum_y);
-  if (lane == 0) {
-    float* dst = sums + ((size_t)sc.level * P.T.B + sc.b) * 2;
-    atomicAdd(dst, sum_x);
-    atomicAdd(dst + 1, sum_y);
+  cp_async_wait<0>();
   }
+  const float acc[2] = {warp_sum(sum_x), warp_sum(sum_y)};
+  block_accumulate<2, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 2 : nullptr);
 }
 
 __global__ void smooth_finalize_kernel(const __grid_constant__ SmoothParams P, const float* __restrict__ sums,
@@ -139,10 +164,18 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
   float sy[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};    // sy rows m-2, m-1, m   (m = r-1)
   float gxr[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // x-part of the gradient, rows r-2, r-1, r
 
-  float nxt[5];
-  load_row(fb, ib, plane, W, sc.y0 - 2, H, sc.col, col_in, nxt);
+  __shared__ float ring_s[kWarpsPerBlock][kDepth * kRowVals * 32];
+  float* ring = ring_s[threadIdx.x >> 5] + lane;
+  const int colc = min(max(sc.col, 0), W - 1);
+#pragma unroll
+  for (int i = 0; i < kDepth - 1; ++i) fetch_row(ring, i, fb, ib, plane, W, sc.y0 - 2 + i, H, colc, col_in);
+  int slot = 0;
   for (int r = sc.y0 - 2; r <= sc.y1 + 1; ++r) {
     const bool inb = col_in && r >= 0 && r < H;
+    fetch_row(ring, slot == 0 ? kDepth - 1 : slot - 1, fb, ib, plane, W, r + kDepth - 1, H, colc, col_in);
+    float nxt[kRowVals];
+    take_row(ring, slot, nxt);
+    slot = slot + 1 == kDepth ? 0 : slot + 1;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
@@ -156,7 +189,6 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
       im[0][c] = im[1][c];
       im[1][c] = nxt[2 + c];
     }
-    if (r < sc.y1 + 1) load_row(fb, ib, plane, W, r + 1, H, sc.col, col_in, nxt);
     // x part for row r
     float ir[3];
 #pragma unroll
@@ -187,6 +219,7 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
       for (int k = 0; k < 2; ++k) gb[o + k * plane] = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) * 0.05f;
     }
   }
+  cp_async_wait<0>();
 }
 
 int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, int B, int Bimg, int halo, bool bwd,
@@ -240,13 +273,15 @@ __device__ __forceinline__ void consis_load(const float* __restrict__ base, int 
   }
 }
 
+constexpr int kConsisFwdWarps = 8;   // forward: 8 warps share one RED pair (block_accumulate)
+
 template <int VEC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kConsisFwdWarps * 32)
 consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ sums) {
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  int level, b, px0;
-  if (!locate_chunk(P, gw, level, b, px0)) return;
+  const int gw = blockIdx.x * kConsisFwdWarps + (threadIdx.x >> 5);
+  int level = 0, b = 0, px0 = 0;
+  const bool live_warp = locate_chunk(P, gw, level, b, px0);
   const uof_consis_level& L = P.lv[level];
   const int plane = L.H * L.W;
   const float* ff = L.flow_fwd + (size_t)b * 2 * plane;
@@ -254,19 +289,20 @@ consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ su
   const float* wf = L.weight_fwd + (size_t)b * plane;
   constexpr int NIT = kConsisPxPerWarp / (32 * VEC);
   float ax[NIT][VEC], ay[NIT][VEC], bx[NIT][VEC], by[NIT][VEC], w[NIT][VEC];
+  const int plane_live = live_warp ? plane : 0;      // idle warps load nothing and contribute zeros
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int p = px0 + (it * 32 + lane) * VEC;
-    consis_load<VEC>(ff, p, plane, ax[it]);
-    consis_load<VEC>(ff + plane, p, plane, ay[it]);
-    consis_load<VEC>(fb, p, plane, bx[it]);
-    consis_load<VEC>(fb + plane, p, plane, by[it]);
-    consis_load<VEC>(wf, p, plane, w[it]);
+    consis_load<VEC>(ff, p, plane_live, ax[it]);
+    consis_load<VEC>(ff + plane, p, plane_live, ay[it]);
+    consis_load<VEC>(fb, p, plane_live, bx[it]);
+    consis_load<VEC>(fb + plane, p, plane_live, by[it]);
+    consis_load<VEC>(wf, p, plane_live, w[it]);
   }
   float num = 0.0f, den = 0.0f;
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
-    const bool live = px0 + (it * 32 + lane) * VEC < plane;
+    const bool live = px0 + (it * 32 + lane) * VEC < plane_live;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const float occ = live ? 1.0f - w[it][v] : 0.0f;                                               // :187
@@ -276,13 +312,8 @@ consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ su
       den += occ;
     }
   }
-  num = warp_sum(num);
-  den = warp_sum(den);
-  if (lane == 0) {
-    float* dst = sums + ((size_t)level * P.B + b) * 2;
-    atomicAdd(dst, num);
-    atomicAdd(dst + 1, den);
-  }
+  const float acc[2] = {warp_sum(num), warp_sum(den)};
+  block_accumulate<2, kConsisFwdWarps>(acc, live_warp ? sums + ((size_t)level * P.B + b) * 2 : nullptr);
 }
 
 __global__ void consis_finalize_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums,
@@ -419,9 +450,9 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
   if (P.vec4)
-    consis_fwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+    consis_fwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kConsisFwdWarps), kConsisFwdWarps * 32, 0, stream>>>(P, sums);
   else
-    consis_fwd_kernel<1><<<ceil_div(P.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+    consis_fwd_kernel<1><<<ceil_div(P.warp_begin[nlevels], kConsisFwdWarps), kConsisFwdWarps * 32, 0, stream>>>(P, sums);
   consis_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
   count_launch(2);
   return check_launch("consis_loss_fwd");

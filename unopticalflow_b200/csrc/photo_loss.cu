@@ -57,12 +57,15 @@ __device__ __forceinline__ PixelWeights pixel_weights(const float* px) {
   return o;
 }
 
-__device__ __forceinline__ void load_pixel(const uof_photo_level& L, unsigned off, unsigned plane, bool inb, float* px) {
+// Unconditional loads from a clamped (always valid) offset: the caller zeroes the weights of out-of-image pixels, which
+// zeroes everything derived from px.  (Predicated zero-filling loads made ptxas copy the just-loaded registers, so the
+// prefetch of the next row stalled the current one.)
+__device__ __forceinline__ void load_pixel(const uof_photo_level& L, unsigned off, unsigned plane, float* px) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    px[c] = inb ? __ldg(L.img + off + c * plane) : 0.0f;
-    px[3 + c] = inb ? __ldg(L.warped_l + off + c * plane) : 0.0f;
-    px[6 + c] = inb ? __ldg(L.warped_r + off + c * plane) : 0.0f;
+    px[c] = __ldg(L.img + off + c * plane);
+    px[3 + c] = __ldg(L.warped_l + off + c * plane);
+    px[6 + c] = __ldg(L.warped_r + off + c * plane);
   }
 }
 
@@ -82,11 +85,11 @@ struct SsimTerms {
   float Sx, Sy, A1, A2, B1, B2, invD, S;
 };
 
-__device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float* s1, const float* s2) {
+// S = {Sx, Sy, Sxx, Syy, Sxy}: raw sums over the 3x3 window
+__device__ __forceinline__ SsimTerms ssim_from_total(float Sx, float Sy, float Sxx, float Syy, float Sxy) {
   SsimTerms t;
-  t.Sx = s0[0] + s1[0] + s2[0];
-  t.Sy = s0[1] + s1[1] + s2[1];
-  const float Sxx = s0[2] + s1[2] + s2[2], Syy = s0[3] + s1[3] + s2[3], Sxy = s0[4] + s1[4] + s2[4];
+  t.Sx = Sx;
+  t.Sy = Sy;
   const float pxy = t.Sx * t.Sy, pxx = t.Sx * t.Sx, pyy = t.Sy * t.Sy;
   t.A1 = fmaf(2.0f, pxy, C1x81);
   t.A2 = fmaf(2.0f, fmaf(9.0f, Sxy, -pxy), C2x81);
@@ -97,47 +100,52 @@ __device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float
   return t;
 }
 
+__device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float* s1, const float* s2) {
+  return ssim_from_total(s0[0] + s1[0] + s2[0], s0[1] + s1[1] + s2[1], s0[2] + s1[2] + s2[2], s0[3] + s1[3] + s2[3],
+                         s0[4] + s1[4] + s2[4]);
+}
+
 // -------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   Strip sc;
-  if (!locate_strip<1>(P.T, gw, lane, sc)) return;
+  const bool live = locate_strip<1>(P.T, gw, lane, sc);   // idle warps still join the block reduction at the end
+  if (!live) sc.level = sc.b = sc.col = sc.y0 = sc.y1 = 0;
   const uof_photo_level& L = P.lv[sc.level];
   const int H = L.H, W = L.W;
   const unsigned plane = (unsigned)(H * W);
   const unsigned img_base = (unsigned)sc.b * 3u * plane, map_base = (unsigned)sc.b * plane;
   const bool col_in = sc.col >= 0 && sc.col < W;
   const bool col_out = col_in && lane >= 1 && lane <= 30;
-  const int colc = max(sc.col, 0);
+  const int colc = min(max(sc.col, 0), W - 1);
 
-  float ring[3][2][3][5];   // [row slot][direction][channel][moment]
+  // Vertical 3-tap sums without a 3-row ring: per map keep last[] = h-sums of row r-1 and pair[] = h(r-2) + h(r-1);
+  // row r then gives the window total pair + h(r) -- the same (s0 + s1) + s2 association as a ring, so results are
+  // bit-identical -- with 60 live registers instead of 90 and no slot rotation (the ring version spilled at the
+  // 128-register cap of 4 blocks/SM).
+  float last[2][3][5], pair[2][3][5];   // [direction][channel][moment]
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int d = 0; d < 2; ++d)
 #pragma unroll
-    for (int d = 0; d < 2; ++d)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) ring[a][d][c][k] = 0.0f;
+      for (int k = 0; k < 5; ++k) last[d][c][k] = pair[d][c][k] = 0.0f;
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-  const int r_begin = sc.y0 - 1, r_end = sc.y1;
-  float nxt[9];
-  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, col_in && r_begin >= 0, nxt);
+  const int r_begin = sc.y0 - 1, r_end = live ? sc.y1 : r_begin - 1;
+  float nxt[9];         // next row, prefetched one iteration ahead
+  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, nxt);
 
-  for (int rb = r_begin; rb <= r_end; rb += 3) {
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int r = rb + u;
-      if (r > r_end) break;
+  for (int r = r_begin; r <= r_end; ++r) {
+    {
       const bool inb = col_in && r >= 0 && r < H;
       const unsigned off = (unsigned)max(r, 0) * W + colc;
       float px[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) px[k] = nxt[k];
-      if (r < r_end) load_pixel(L, img_base + (unsigned)min(r + 1, H - 1) * W + colc, plane, col_in && r + 1 < H, nxt);
+      load_pixel(L, img_base + (unsigned)min(r + 1, H - 1) * W + colc, plane, nxt);
 
       PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
       if (inb) pw = pixel_weights(px);
@@ -151,30 +159,32 @@ photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__
         if (L.diff_l) L.diff_l[map_base + off] = pw.dl;
         if (L.diff_r) L.diff_r[map_base + off] = pw.dr;
       }
+      const bool emit = r - 1 >= sc.y0 && col_out;      // row q = r-1 now has its full 3x3 window
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
         const float wd = d ? pw.wr : pw.wl;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) hsum_moments(px[c] * wd, px[3 + 3 * d + c] * wd, ring[u][d][c]);
-      }
-      // row q = r-1 now has its full 3x3 window (slots (u+1)%3, (u+2)%3, u hold rows q-1, q, q+1)
-      if (r - 1 >= sc.y0 && col_out) {
-#pragma unroll
-        for (int d = 0; d < 2; ++d)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const SsimTerms t = ssim_from_sums(ring[(u + 1) % 3][d][c], ring[(u + 2) % 3][d][c], ring[u][d][c]);
+        for (int c = 0; c < 3; ++c) {
+          float h[5];
+          hsum_moments(px[c] * wd, px[3 + 3 * d + c] * wd, h);
+          float* pr = pair[d][c];
+          float* la = last[d][c];
+          if (emit) {
+            const SsimTerms t = ssim_from_total(pr[0] + h[0], pr[1] + h[1], pr[2] + h[2], pr[3] + h[3], pr[4] + h[4]);
             acc[4 + d] += __saturatef(fmaf(-0.5f, t.S, 0.5f));   // clamp((1-S)/2, 0, 1), model_flow_paper.py:144
           }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            pr[k] = la[k] + h[k];
+            la[k] = h[k];
+          }
+        }
       }
     }
   }
-  float* dst = sums + ((size_t)sc.level * P.T.B + sc.b) * 6;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float v = warp_sum(acc[k]);
-    if (lane == 0) atomicAdd(dst + k, v);
-  }
+  for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+  block_accumulate<6, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 6 : nullptr);
 }
 
 // loss_pixel[b] = sum_l sum_d mean(d*w)/(mean(w)+eps);  loss_ssim[b] likewise (model_flow_paper.py:94-98,141-147)
@@ -212,7 +222,7 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
   const unsigned img_base = (unsigned)sc.b * 3u * plane;
   const bool col_in = sc.col >= 0 && sc.col < W;
   const bool col_out = col_in && lane >= 2 && lane <= 29;
-  const int colc = max(sc.col, 0);
+  const int colc = min(max(sc.col, 0), W - 1);
   float* gout = dir ? L.gwarped_r : L.gwarped_l;
 
   const float n = (float)H * (float)W;
@@ -241,7 +251,7 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
 
   const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
   float nxt[9];
-  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, col_in && r_begin >= 0, nxt);
+  load_pixel(L, img_base + (unsigned)max(r_begin, 0) * W + colc, plane, nxt);
 
   for (int rb = r_begin; rb <= r_end; rb += 3) {
 #pragma unroll
@@ -253,8 +263,7 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
       float px[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) px[k] = nxt[k];
-      if (r < r_end) load_pixel(L, img_base + (unsigned)min(max(r + 1, 0), H - 1) * W + colc, plane,
-                                col_in && r + 1 >= 0 && r + 1 < H, nxt);
+      if (r < r_end) load_pixel(L, img_base + (unsigned)min(max(r + 1, 0), H - 1) * W + colc, plane, nxt);
       PixelWeights pw = {0.f, 0.f, 0.f, 0.f};
       if (inb) pw = pixel_weights(px);
       const float wd = dir ? pw.wr : pw.wl;
@@ -322,6 +331,7 @@ photo_loss_bwd_kernel(const __grid_constant__ PhotoParams P, const float* __rest
 // runs at ~70 registers / 28+ resident warps per SM instead of 151 / 12 -- the fused-direction kernel above was
 // latency/issue bound at 60 % issue utilisation (ncu, profiles/).
 constexpr int kSplitWarps = 6;
+constexpr int kPairDepth = 4;      // rows in the cp.async ring of the pixel-pair kernel
 
 __global__ void __launch_bounds__(kSplitWarps * 32)
 photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
@@ -337,7 +347,7 @@ photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* 
   const unsigned ch_base = ((unsigned)sc.b * 3u + (unsigned)c) * plane, map_base = (unsigned)sc.b * plane;
   const bool col_in = sc.col >= 0 && sc.col < W;
   const bool col_out = col_in && lane >= 2 && lane <= 29;
-  const int colc = max(sc.col, 0);
+  const int colc = min(max(sc.col, 0), W - 1);
   const float* __restrict__ img = L.img + ch_base;
   const float* __restrict__ wrp = (dir ? L.warped_r : L.warped_l) + ch_base;
   const float* __restrict__ wgt = (dir ? L.weight_r : L.weight_l) + map_base;
@@ -361,15 +371,13 @@ photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* 
 
   const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
   // three rows of (I, W, w) are kept in flight: a row is ~100 instructions of work, far less than a DRAM round trip
-  float pre[3][3];
+  float pre[3][3];   // two rows in flight in a three-slot ring (see pair kernel)
 #pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int r = r_begin + u;
-    const bool inb = col_in && r >= 0 && r < H && r <= r_end;
-    const unsigned o = (unsigned)max(r, 0) * W + colc;
-    pre[u][0] = inb ? __ldg(img + o) : 0.0f;
-    pre[u][1] = inb ? __ldg(wrp + o) : 0.0f;
-    pre[u][2] = inb ? __ldg(wgt + o) : 0.0f;
+  for (int u = 0; u < 2; ++u) {
+    const unsigned o = (unsigned)min(max(r_begin + u, 0), H - 1) * W + colc;    // unconditional, clamped (see pair kernel)
+    pre[u][0] = __ldg(img + o);
+    pre[u][1] = __ldg(wrp + o);
+    pre[u][2] = __ldg(wgt + o);
   }
   for (int rb = r_begin; rb <= r_end; rb += 3) {
 #pragma unroll
@@ -377,14 +385,14 @@ photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* 
       const int r = rb + u;
       if (r > r_end) break;
       // ring slots: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
-      const float vI = pre[u][0], vW = pre[u][1], vw = pre[u][2];
+      const bool row_in = col_in && r >= 0 && r < H;
+      const float vI = row_in ? pre[u][0] : 0.0f, vW = row_in ? pre[u][1] : 0.0f, vw = row_in ? pre[u][2] : 0.0f;
       {
-        const int rn = r + 3;
-        const bool inb = col_in && rn >= 0 && rn < H && rn <= r_end;
-        const unsigned o = (unsigned)min(max(rn, 0), H - 1) * W + colc;
-        pre[u][0] = inb ? __ldg(img + o) : 0.0f;
-        pre[u][1] = inb ? __ldg(wrp + o) : 0.0f;
-        pre[u][2] = inb ? __ldg(wgt + o) : 0.0f;
+        const unsigned o = (unsigned)min(r + 2, H - 1) * W + colc;
+        float* nx = pre[(u + 2) % 3];
+        nx[0] = __ldg(img + o);
+        nx[1] = __ldg(wrp + o);
+        nx[2] = __ldg(wgt + o);
       }
       const float df = vI - vW;
       const float sg = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
@@ -471,7 +479,7 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
   const unsigned plane = (unsigned)(H * W);
   const bool pin = sc.col >= 0 && sc.col < W;            // W even: the pair is entirely inside or outside
   const bool pout = pin && lane >= 1 && lane <= 30;
-  const unsigned colc = (unsigned)max(sc.col, 0);
+  const unsigned colc = (unsigned)min(max(sc.col, 0), W - 2);   // clamped: loads are unconditional
   const unsigned ch_base = ((unsigned)sc.b * 3u + (unsigned)c) * plane + colc, map_base = (unsigned)sc.b * plane + colc;
   const float* __restrict__ img = L.img + ch_base;
   const float* __restrict__ wrp = (dir ? L.warped_r : L.warped_l) + ch_base;
@@ -497,33 +505,34 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
     }
 
   const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
-  float2 pre[3][3];       // three rows in flight: (I, W, w) pairs
+  // Row pipeline: a per-warp shared-memory ring of kPairDepth rows x (I, W, w) float2 pairs, kPairDepth-1 rows kept in
+  // flight with 8-byte cp.async (zero-filled outside the image).  Register prefetching (three rows of float2 in
+  // `pre[3][3]`) left 32 % of the samples on long-scoreboard stalls: ptxas hoists the next LDGs above the last use of the
+  // registers they replace and then copies the just-loaded values (ncu source page, round 2).
+  __shared__ float2 ring_s[kSplitWarps][kPairDepth * 3 * 32];
+  float2* ring = ring_s[role] + lane;
+  auto fetch = [&](int r, int slot) {
+    const bool inb = pin && r >= 0 && r < H;
+    const unsigned o = (unsigned)min(max(r, 0), H - 1) * W;
+    float2* d = ring + slot * (3 * 32);
+    cp_async_8(d, img + o, inb);
+    cp_async_8(d + 32, wrp + o, inb);
+    cp_async_8(d + 64, wgt + o, inb);
+    cp_async_commit();
+  };
 #pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int r = r_begin + u;
-    const bool inb = pin && r >= 0 && r < H && r <= r_end;
-    const unsigned o = (unsigned)max(r, 0) * W;
-    const float2 z = make_float2(0.f, 0.f);
-    pre[u][0] = inb ? __ldg(reinterpret_cast<const float2*>(img + o)) : z;
-    pre[u][1] = inb ? __ldg(reinterpret_cast<const float2*>(wrp + o)) : z;
-    pre[u][2] = inb ? __ldg(reinterpret_cast<const float2*>(wgt + o)) : z;
-  }
+  for (int i = 0; i < kPairDepth - 1; ++i) fetch(r_begin + i, i);
+  int slot = 0;
   for (int rb = r_begin; rb <= r_end; rb += 3) {
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
       const int r = rb + u;
       if (r > r_end) break;
-      // ring slots: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
-      const float2 vI = pre[u][0], vW = pre[u][1], vw = pre[u][2];
-      {
-        const int rn = r + 3;
-        const bool inb = pin && rn < H && rn <= r_end;     // rn >= 1 here
-        const unsigned o = (unsigned)min(rn, H - 1) * W;
-        const float2 z = make_float2(0.f, 0.f);
-        pre[u][0] = inb ? __ldg(reinterpret_cast<const float2*>(img + o)) : z;
-        pre[u][1] = inb ? __ldg(reinterpret_cast<const float2*>(wrp + o)) : z;
-        pre[u][2] = inb ? __ldg(reinterpret_cast<const float2*>(wgt + o)) : z;
-      }
+      // ring slots of the moments: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
+      fetch(r + kPairDepth - 1, slot == 0 ? kPairDepth - 1 : slot - 1);
+      cp_async_wait<kPairDepth - 1>();
+      const float2 vI = ring[slot * 96], vW = ring[slot * 96 + 32], vw = ring[slot * 96 + 64];
+      slot = slot + 1 == kPairDepth ? 0 : slot + 1;
       const float d0 = vI.x - vW.x, d1 = vI.y - vW.y;
       wl1[u][0][0] = vw.x;
       wl1[u][1][0] = vw.y;
@@ -566,6 +575,7 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm,

@@ -38,27 +38,26 @@ struct RunCoord {
   bool live;
 };
 
-// warp index -> (batch, channel chunk, row, run of 32*PXT pixels)
-__device__ __forceinline__ RunCoord locate_run(long long gw, int runs_per_row, int H, int nchunk, int B, int run_px) {
+// Grid = (runs per row, ceil(H / kWarps), B * nchunk): block (run, row group, b * nchunk + chunk), warp = row within
+// the group.  No per-thread division: the first version decoded a linear 64-bit warp index with three long-long
+// div/mod pairs, ~150 of the ~580 instructions a warp executed for an image warp (ncu source page, round 2).
+__device__ __forceinline__ RunCoord locate_run(int H, int nchunk, int run_px) {
   RunCoord rc;
-  const int run = (int)(gw % runs_per_row);
-  long long r = gw / runs_per_row;
-  rc.y = (int)(r % H);
-  r /= H;
-  rc.chunk = (int)(r % nchunk);
-  rc.b = (int)(r / nchunk);
-  rc.x0 = run * run_px;
-  rc.live = rc.b < B;
+  rc.y = (int)blockIdx.y * kWarps + (int)(threadIdx.x >> 5);
+  rc.b = (int)(blockIdx.z / (unsigned)nchunk);           // block-uniform
+  rc.chunk = (int)blockIdx.z - rc.b * nchunk;
+  rc.x0 = (int)blockIdx.x * run_px;
+  rc.live = rc.y < H;
   return rc;
 }
 
 // ---------------------------------------------------------------------------------- NCHW fwd
-template <int PXT>
+template <int PXT, int UNR>
 __global__ void __launch_bounds__(kWarps * 32)
 warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out, int B, int C,
                      int H, int W, int nchunk, int runs_per_row, int use_mask, int align_corners) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run((long long)blockIdx.x * kWarps + (threadIdx.x >> 5), runs_per_row, H, nchunk, B, 32 * PXT);
+  const RunCoord rc = locate_run(H, nchunk, 32 * PXT);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const float* fb = flow + (size_t)rc.b * 2 * plane + (size_t)rc.y * W;
@@ -88,7 +87,7 @@ warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow
   const int c0 = rc.chunk * cch, c1 = min(C, c0 + cch);
   const float* xp = x + ((size_t)rc.b * C + c0) * plane;
   float* op = out + ((size_t)rc.b * C + c0) * plane + (size_t)rc.y * W + rc.x0 + lane;
-#pragma unroll 2
+#pragma unroll UNR
   for (int c = c0; c < c1; ++c, xp += plane, op += plane) {
     float v[PXT][4];
 #pragma unroll
@@ -106,13 +105,13 @@ warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow
 
 // ---------------------------------------------------------------------------------- NCHW bwd
 // ATOMIC_GFLOW: several channel chunks contribute to the same gflow element (gflow zero-filled by the host).
-template <int PXT, bool NEED_GX, bool ATOMIC_GFLOW>
+template <int PXT, bool NEED_GX, bool ATOMIC_GFLOW, int UNR>
 __global__ void __launch_bounds__(kWarps * 32)
 warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x, const float* __restrict__ flow,
                      float* __restrict__ gx, float* __restrict__ gflow, int B, int C, int H, int W, int nchunk,
                      int runs_per_row, int use_mask, int align_corners, float sx, float sy) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run((long long)blockIdx.x * kWarps + (threadIdx.x >> 5), runs_per_row, H, nchunk, B, 32 * PXT);
+  const RunCoord rc = locate_run(H, nchunk, 32 * PXT);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const size_t row = (size_t)rc.y * W;
@@ -165,7 +164,7 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
   float gix[PXT], giy[PXT];
 #pragma unroll
   for (int k = 0; k < PXT; ++k) gix[k] = giy[k] = 0.0f;
-#pragma unroll 2
+#pragma unroll UNR
   for (int c = c0; c < c1; ++c, xp += plane, gp += plane) {
     float g[PXT], v[PXT][4];
 #pragma unroll
@@ -354,9 +353,11 @@ extern "C" int uof_warp_fwd(const float* x, const float* flow, float* out, int B
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, false), runs = ceil_div(W, 32 * pxt);
-    const unsigned blocks = (unsigned)ceil_div_ll((long long)B * nchunk * H * runs, kWarps);
-#define UOF_FWD(P) warp_fwd_nchw_kernel<P><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, runs, use_mask, align_corners)
-    if (pxt == 4) UOF_FWD(4); else if (pxt == 2) UOF_FWD(2); else UOF_FWD(1);
+    UOF_REQUIRE((long long)B * nchunk <= 65535 && ceil_div(H, kWarps) <= 65535, "warp_fwd: grid too large (B*chunks=%lld)", (long long)B * nchunk);
+    const dim3 blocks(runs, ceil_div(H, kWarps), B * nchunk);
+#define UOF_FWD(P, U) warp_fwd_nchw_kernel<P, U><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, runs, use_mask, align_corners)
+    static const int unr = env_int("UOF_WARP_UNROLL");
+    if (pxt == 4) UOF_FWD(4, 2); else if (pxt == 2) { if (unr == 4) UOF_FWD(2, 4); else UOF_FWD(2, 2); } else { if (unr == 4) UOF_FWD(1, 4); else UOF_FWD(1, 2); }
 #undef UOF_FWD
   } else {
     const long long npix = (long long)B * H * W, total = npix * (C / 4);
@@ -372,10 +373,18 @@ template <int PXT>
 static void launch_bwd_nchw(const float* gout, const float* x, const float* flow, float* gx, float* gflow, int B, int C,
                             int H, int W, int nchunk, int runs, int use_mask, int align_corners, float sx, float sy,
                             cudaStream_t stream) {
-  const unsigned blocks = (unsigned)ceil_div_ll((long long)B * nchunk * H * runs, kWarps);
-#define UOF_LAUNCH(GX, AT)                                                                                        \
-  warp_bwd_nchw_kernel<PXT, GX, AT><<<blocks, kWarps * 32, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, \
-                                                                        runs, use_mask, align_corners, sx, sy)
+  const dim3 blocks(runs, ceil_div(H, kWarps), B * nchunk);
+  static const int unr = env_int("UOF_WARP_UNROLL");
+#define UOF_LAUNCH(GX, AT)                                                                                              \
+  do {                                                                                                                  \
+    if (unr == 4 && PXT == 1)                                                                                           \
+      warp_bwd_nchw_kernel<PXT, GX, AT, (PXT == 1 ? 4 : 2)><<<blocks, kWarps * 32, 0, stream>>>(                         \
+          gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy);                         \
+    else                                                                                                                \
+      warp_bwd_nchw_kernel<PXT, GX, AT, 2><<<blocks, kWarps * 32, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W,    \
+                                                                               nchunk, runs, use_mask, align_corners,  \
+                                                                               sx, sy);                                 \
+  } while (0)
   if (gx) {
     if (nchunk > 1) UOF_LAUNCH(true, true); else UOF_LAUNCH(true, false);
   } else {
@@ -393,6 +402,7 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
   if (gx) UOF_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * C * H * W * sizeof(float), stream));
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, true), runs = ceil_div(W, 32 * pxt);
+    UOF_REQUIRE((long long)B * nchunk <= 65535 && ceil_div(H, kWarps) <= 65535, "warp_bwd: grid too large (B*chunks=%lld)", (long long)B * nchunk);
     if (nchunk > 1) UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
     if (pxt == 4)
       launch_bwd_nchw<4>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);

@@ -178,11 +178,16 @@ def cases(B=8, H=256, W=832):
            [lambda f=f, o=o: _lib.call('uof_splat_fwd', None, ops._p(f), ops._p(o), B2, H, W, 1, ops._stream(anchor)) for f, o in zip(fl_nhwc, rm)])
 
 
-def run(peak_gbs, B=8, H=256, W=832, only=None):
+def run(peak_gbs, B=8, H=256, W=832, only=None, once=False):
     _lib.load()
     rows = []
     for name, nbytes, fns in cases(B, H, W):
         if only and only not in name:
+            continue
+        if once:       # one plain launch per case on cold buffers: the mode `ncu --set full` is run on
+            fns[-1]()
+            torch.cuda.synchronize()
+            print('once', name)
             continue
         us = _time_graph(fns)
         gbs = nbytes / (us * 1e-6) / 1e9
@@ -205,8 +210,9 @@ if __name__ == '__main__':
     ap.add_argument('--only', default=None)
     ap.add_argument('--peak', type=float, default=6531.9)
     ap.add_argument('--json', default=None)
+    ap.add_argument('--once', action='store_true', help='launch every case once, untimed (for ncu --set full)')
     a = ap.parse_args()
-    rows = run(a.peak, only=a.only)
+    rows = run(a.peak, only=a.only, once=a.once)
     for r_ in rows:
         print('%-58s %9.2f us %9.2f MB %8.1f GB/s  frac %.3f' % (r_['kernel'], r_['avg_us'], r_['alg_mb'], r_['achieved_gbs'], r_['frac']))
     if a.json:
