@@ -81,22 +81,24 @@ __device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src, bool valid) {
   unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   int bytes = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src, bool valid) {
   unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   int bytes = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src, bool valid) {
   unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   int bytes = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// "memory" clobbers: without them the compiler may move ordinary shared-memory loads across the wait (reading a slot
+// before its copy has landed) or across the next copy into the same slot.
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 // ---- bilinear sampling coordinates of warp_flow (net_utils.py:39-46 + ATen grid_sampler) ---------

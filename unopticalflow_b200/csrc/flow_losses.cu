@@ -7,6 +7,8 @@
 // its pixel once per row, x-neighbours come from warp shuffles, y-neighbours from a 3-row register
 // ring; all pyramid levels and both flow directions (flow batch B, image batch Bimg, image index
 // b % Bimg) go in one launch.  Consistency is a pure streaming kernel.
+#include <stdlib.h>
+
 #include "strips.cuh"
 
 namespace uof {
@@ -22,6 +24,9 @@ struct SmoothParams {
 };
 
 __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+// second difference (hi - mid) - (mid - lo) with the reference's roundings (model_flow_paper.py:153-155 applied twice)
+__device__ __forceinline__ float d2(float lo, float mid, float hi) { return __fsub_rn(__fsub_rn(hi, mid), __fsub_rn(mid, lo)); }
 
 // exp(-10 * mean_c |a_c - b_c|)   (model_flow_paper.py:159-160)
 __device__ __forceinline__ float edge_weight(const float* a, const float* b) {
@@ -94,7 +99,7 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
       f[1][k] = f[2][k];
-      f[2][k] = nxt[k] * 0.05f;   // :174 flow/20.0
+      f[2][k] = __fmul_rn(nxt[k], 0.05f);   // :174 flow/20.0 (no FMA contraction, see take_quad)
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -109,13 +114,13 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const float fl = __shfl_up_sync(kFullMask, f[2][k], 1), fr = __shfl_down_sync(kFullMask, f[2][k], 1);
-      d2x += fabsf((fr - f[2][k]) - (f[2][k] - fl));   // :153-155,163-164
+      d2x += fabsf(d2(fl, f[2][k], fr));   // :153-155,163-164
     }
     if (col_out && r >= sc.y0 && r < sc.y1 && sc.col >= 1 && sc.col <= W - 2) sum_x = fmaf(edge_weight(ir, im[1]), d2x, sum_x);
     // y term centred on row m = r-1: rows m-1, m, m+1 are f[0], f[1], f[2]
     const int m = r - 1;
     if (col_out && m >= sc.y0 && m >= 1 && m <= H - 2) {
-      const float d2y = fabsf((f[2][0] - f[1][0]) - (f[1][0] - f[0][0])) + fabsf((f[2][1] - f[1][1]) - (f[1][1] - f[0][1]));
+      const float d2y = fabsf(d2(f[0][0], f[1][0], f[2][0])) + fabsf(d2(f[0][1], f[1][1], f[2][1]));
       sum_y = fmaf(edge_weight(im[1], im[0]), d2y, sum_y);
     }
   }
@@ -180,7 +185,7 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
     for (int k = 0; k < 2; ++k) {
       f[0][k] = f[1][k];
       f[1][k] = f[2][k];
-      f[2][k] = nxt[k] * 0.05f;
+      f[2][k] = __fmul_rn(nxt[k], 0.05f);
       gxr[0][k] = gxr[1][k];
       gxr[1][k] = gxr[2][k];
     }
@@ -198,7 +203,7 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const float fl = __shfl_up_sync(kFullMask, f[2][k], 1), fr = __shfl_down_sync(kFullMask, f[2][k], 1);
-      const float s = wx * sgn((fr - f[2][k]) - (f[2][k] - fl));
+      const float s = wx * sgn(d2(fl, f[2][k], fr));
       gxr[2][k] = __shfl_up_sync(kFullMask, s, 1) - 2.0f * s + __shfl_down_sync(kFullMask, s, 1);
     }
     // y part: sy at row m = r-1
@@ -209,7 +214,7 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
     for (int k = 0; k < 2; ++k) {
       sy[0][k] = sy[1][k];
       sy[1][k] = sy[2][k];
-      sy[2][k] = wy * sgn((f[2][k] - f[1][k]) - (f[1][k] - f[0][k]));
+      sy[2][k] = wy * sgn(d2(f[0][k], f[1][k], f[2][k]));
     }
     // output row p = r-2: sy rows p-1, p, p+1 are sy[0..2]; x part is gxr[0]
     const int p = r - 2;
@@ -222,8 +227,258 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
   cp_async_wait<0>();
 }
 
+
+// ------------------------------------------------------------------------------ smooth, quad layout
+// Same math, four adjacent columns per lane (W % 4 == 0, 16-byte aligned planes): a strip is 128 columns wide, lanes
+// 1..30 own outputs (120 columns) and lanes 0 / 31 are the column halo.  The one-pixel-per-lane kernels above are
+// instruction-issue bound (ncu, round 2: ~140 instructions per warp-row of 30 pixels, 43 % of them integer address
+// and predicate work, issue slots 75 % busy, DRAM at 25 %); a quad amortises addressing, predicates and the
+// neighbour shuffles over four pixels (7 SHFL per 4 px instead of 7 per px) and moves rows with 16-byte cp.async
+// (five LDGSTS.128 + five LDS.128 per quad-row, zero-filled outside the image) through a per-warp three-slot ring.
+// The row loop is unrolled by 3 so that ring slots and the 3-row register rings are statically indexed.
+constexpr int kQDepth = 3;
+constexpr float kEdgeLog2 = (-10.0f / 3.0f) * 1.4426950408889634f;   // exp(-10/3 s) = 2^(kEdgeLog2 s)
+
+__device__ __forceinline__ float ex2_ftz(float x) {    // arguments are <= 0: results in (0, 1], tiny ones flush to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct QuadRow {
+  float f[4][2];     // flow / 20
+  float im[4][3];
+};
+
+__device__ __forceinline__ void fetch_quad(float4* ring, int slot, const float* __restrict__ fb, const float* __restrict__ ib,
+                                           size_t plane, int W, int r, int H, int colc, bool qin) {
+  const bool inb = qin && r >= 0 && r < H;
+  const size_t off = (size_t)min(max(r, 0), H - 1) * W + colc;
+  float4* d = ring + slot * (kRowVals * 32);
+  cp_async_16(reinterpret_cast<float*>(d), fb + off, inb);
+  cp_async_16(reinterpret_cast<float*>(d + 32), fb + off + plane, inb);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) cp_async_16(reinterpret_cast<float*>(d + (2 + c) * 32), ib + off + c * plane, inb);
+  cp_async_commit();
+}
+
+__device__ __forceinline__ void take_quad(const float4* ring, int slot, QuadRow& q) {
+  cp_async_wait<kQDepth - 1>();
+  const float4* d = ring + slot * (kRowVals * 32);
+  const float4 a = d[0], b = d[32];
+  // :174 flow/20.0.  __fmul_rn / d2(): no FMA contraction -- the decoder's flows are bilinearly up-sampled, i.e. piecewise
+  // linear, so their second differences are pure rounding noise over large areas and the backward pass takes the SIGN of
+  // that noise: it has to round exactly like the reference's separate mul / sub / sub.
+  q.f[0][0] = __fmul_rn(a.x, 0.05f); q.f[1][0] = __fmul_rn(a.y, 0.05f); q.f[2][0] = __fmul_rn(a.z, 0.05f); q.f[3][0] = __fmul_rn(a.w, 0.05f);
+  q.f[0][1] = __fmul_rn(b.x, 0.05f); q.f[1][1] = __fmul_rn(b.y, 0.05f); q.f[2][1] = __fmul_rn(b.z, 0.05f); q.f[3][1] = __fmul_rn(b.w, 0.05f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 t = d[(2 + c) * 32];
+    q.im[0][c] = t.x; q.im[1][c] = t.y; q.im[2][c] = t.z; q.im[3][c] = t.w;
+  }
+}
+
+__device__ __forceinline__ float edge_l1(const float* a, const float* b) {
+  return fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2]);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+smooth_fwd_quad_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums) {
+  __shared__ float4 ring_s[kWarpsPerBlock][kQDepth * kRowVals * 32];
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Strip sc;
+  const bool live = locate_strip<4, 4>(P.T, gw, lane, sc);   // idle warps still join the block reduction below
+  if (!live) sc.level = sc.b = sc.col = sc.y0 = sc.y1 = 0;
+  const uof_smooth_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const float* fb = L.flow + (size_t)sc.b * 2 * plane;
+  const float* ib = L.img + (size_t)(sc.b % P.Bimg) * 3 * plane;
+  const bool qin = sc.col >= 0 && sc.col < W;             // W % 4 == 0: the quad is entirely inside or outside
+  const bool lane_out = qin && lane >= 1 && lane <= 30;
+  const int colc = min(max(sc.col, 0), W - 4);
+  float mx[4], my;                                         // column validity of the x / y terms as multipliers
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mx[j] = (lane_out && sc.col + j >= 1 && sc.col + j <= W - 2) ? 1.0f : 0.0f;
+  my = lane_out ? 1.0f : 0.0f;
+  float sum_x = 0.0f, sum_y = 0.0f;
+  if (live) {
+    float4* ring = ring_s[threadIdx.x >> 5] + lane;
+    QuadRow q[3];                                          // ring slots: row r -> u, r-1 -> (u+2)%3, r-2 -> (u+1)%3
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        q[a].f[j][0] = q[a].f[j][1] = 0.0f;
+        q[a].im[j][0] = q[a].im[j][1] = q[a].im[j][2] = 0.0f;
+      }
+    const int r_begin = sc.y0 - 1, r_end = sc.y1;
+    fetch_quad(ring, 0, fb, ib, plane, W, r_begin, H, colc, qin);
+    fetch_quad(ring, 1, fb, ib, plane, W, r_begin + 1, H, colc, qin);
+    for (int rb = r_begin; rb <= r_end; rb += 3) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int r = rb + u;
+        if (r > r_end) break;
+        fetch_quad(ring, (u + 2) % 3, fb, ib, plane, W, r + 2, H, colc, qin);
+        QuadRow& c = q[u];
+        const QuadRow& p1 = q[(u + 2) % 3];
+        const QuadRow& p2 = q[(u + 1) % 3];
+        take_quad(ring, u, c);
+        // neighbours across the quad boundary: column -1 from lane-1's last pixel, column 4 from lane+1's first pixel
+        float fl[2], fr[2], ir[3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          fl[k] = __shfl_up_sync(kFullMask, c.f[3][k], 1);
+          fr[k] = __shfl_down_sync(kFullMask, c.f[0][k], 1);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) ir[ch] = __shfl_down_sync(kFullMask, c.im[0][ch], 1);
+        if (r >= sc.y0 && r < sc.y1) {          // x term centred on (r, col)                       :153-155,163-164
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* lf = j == 0 ? fl : c.f[j - 1];
+            const float* rf = j == 3 ? fr : c.f[j + 1];
+            const float* ri = j == 3 ? ir : c.im[j + 1];
+            const float w = ex2_ftz(kEdgeLog2 * edge_l1(ri, c.im[j])) * mx[j];
+            const float dd = fabsf(d2(lf[0], c.f[j][0], rf[0])) + fabsf(d2(lf[1], c.f[j][1], rf[1]));
+            sum_x = fmaf(w, dd, sum_x);
+          }
+        }
+        const int m = r - 1;                    // y term centred on row m: rows m-1, m, m+1 are p2, p1, c
+        if (m >= sc.y0 && m >= 1 && m <= H - 2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float w = ex2_ftz(kEdgeLog2 * edge_l1(c.im[j], p1.im[j])) * my;
+            const float dd = fabsf(d2(p2.f[j][0], p1.f[j][0], c.f[j][0])) + fabsf(d2(p2.f[j][1], p1.f[j][1], c.f[j][1]));
+            sum_y = fmaf(w, dd, sum_y);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+  }
+  const float acc[2] = {warp_sum(sum_x), warp_sum(sum_y)};
+  block_accumulate<2, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 2 : nullptr);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+smooth_bwd_quad_kernel(const __grid_constant__ SmoothParams P, const float* __restrict__ g_loss) {
+  __shared__ float4 ring_s[kWarpsPerBlock][kQDepth * kRowVals * 32];
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Strip sc;
+  if (!locate_strip<4, 4>(P.T, gw, lane, sc)) return;
+  const uof_smooth_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const size_t plane = (size_t)H * W;
+  const float* fb = L.flow + (size_t)sc.b * 2 * plane;
+  const float* ib = L.img + (size_t)(sc.b % P.Bimg) * 3 * plane;
+  float* gb = L.gflow + (size_t)sc.b * 2 * plane;
+  const bool qin = sc.col >= 0 && sc.col < W;
+  const bool lane_out = qin && lane >= 1 && lane <= 30;
+  const int colc = min(max(sc.col, 0), W - 4);
+  const float g = __ldg(g_loss + sc.b);
+  const float cx = g * 0.5f / (2.0f * (float)H * ((float)W - 2.0f));
+  const float cy = qin ? g * 0.5f / (2.0f * ((float)H - 2.0f) * (float)W) : 0.0f;
+  float cxm[4];                                  // cx where the x term exists (1 <= col <= W-2), else 0
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cxm[j] = (qin && sc.col + j >= 1 && sc.col + j <= W - 2) ? cx : 0.0f;
+
+  float4* ring = ring_s[threadIdx.x >> 5] + lane;
+  QuadRow q[3];            // rows r, r-1, r-2 in slots u, (u+2)%3, (u+1)%3
+  float sy[3][4][2];       // sy at rows m = r-1 (slot u), m-1, m-2
+  float gx[3][4][2];       // x part of the gradient at rows r (slot u), r-1, r-2
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[a].f[j][0] = q[a].f[j][1] = 0.0f;
+      q[a].im[j][0] = q[a].im[j][1] = q[a].im[j][2] = 0.0f;
+      sy[a][j][0] = sy[a][j][1] = gx[a][j][0] = gx[a][j][1] = 0.0f;
+    }
+  const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
+  fetch_quad(ring, 0, fb, ib, plane, W, r_begin, H, colc, qin);
+  fetch_quad(ring, 1, fb, ib, plane, W, r_begin + 1, H, colc, qin);
+  for (int rb = r_begin; rb <= r_end; rb += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int r = rb + u;
+      if (r > r_end) break;
+      fetch_quad(ring, (u + 2) % 3, fb, ib, plane, W, r + 2, H, colc, qin);
+      QuadRow& c = q[u];
+      const QuadRow& p1 = q[(u + 2) % 3];
+      const QuadRow& p2 = q[(u + 1) % 3];
+      take_quad(ring, u, c);
+      float fl[2], fr[2], ir[3];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        fl[k] = __shfl_up_sync(kFullMask, c.f[3][k], 1);
+        fr[k] = __shfl_down_sync(kFullMask, c.f[0][k], 1);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) ir[ch] = __shfl_down_sync(kFullMask, c.im[0][ch], 1);
+      // x part of row r: s = cx wx sign(d2x) (zero rows outside the image give sign(0) = 0), then its second difference
+      float s[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* lf = j == 0 ? fl : c.f[j - 1];
+        const float* rf = j == 3 ? fr : c.f[j + 1];
+        const float* ri = j == 3 ? ir : c.im[j + 1];
+        const float w = ex2_ftz(kEdgeLog2 * edge_l1(ri, c.im[j])) * cxm[j];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) s[j][k] = w * sgn(d2(lf[k], c.f[j][k], rf[k]));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float sl = __shfl_up_sync(kFullMask, s[3][k], 1), sr = __shfl_down_sync(kFullMask, s[0][k], 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          gx[u][j][k] = (j == 0 ? sl : s[j - 1][k]) - 2.0f * s[j][k] + (j == 3 ? sr : s[j + 1][k]);
+      }
+      // y part: sy at row m = r-1 from rows m-1, m, m+1 = p2, p1, c
+      const int m = r - 1;
+      const float cym = (m >= 1 && m <= H - 2) ? cy : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = ex2_ftz(kEdgeLog2 * edge_l1(c.im[j], p1.im[j])) * cym;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) sy[u][j][k] = w * sgn(d2(p2.f[j][k], p1.f[j][k], c.f[j][k]));
+      }
+      // output row p = r-2: sy rows p-1, p, p+1 are slots (u+1)%3, (u+2)%3, u; its x part is gx slot (u+1)%3
+      const int p = r - 2;
+      if (p >= sc.y0 && p < sc.y1 && lane_out) {
+        const size_t o = (size_t)p * W + sc.col;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float4 v;
+          float* vp = reinterpret_cast<float*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            vp[j] = (gx[(u + 1) % 3][j][k] + (sy[(u + 1) % 3][j][k] - 2.0f * sy[(u + 2) % 3][j][k] + sy[u][j][k])) * 0.05f;
+          *reinterpret_cast<float4*>(gb + o + k * plane) = v;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// true when every level can use the quad kernels: W % 4 == 0 and 16-byte aligned planes
+bool smooth_quad_ok(const uof_smooth_level* levels, int nlevels, bool bwd) {
+  static const bool off = getenv("UOF_SMOOTH_NO_QUAD") != nullptr;
+  if (off || !levels) return false;
+  for (int l = 0; l < nlevels && l < UOF_MAX_LEVELS; ++l) {
+    uintptr_t bits = reinterpret_cast<uintptr_t>(levels[l].flow) | reinterpret_cast<uintptr_t>(levels[l].img);
+    if (bwd) bits |= reinterpret_cast<uintptr_t>(levels[l].gflow);
+    if ((bits & 15u) || levels[l].W % 4 != 0 || levels[l].W < 4) return false;
+  }
+  return true;
+}
+
 int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, int B, int Bimg, int halo, bool bwd,
-                int blocks_per_sm) {
+                int blocks_per_sm, bool quad = false) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "smooth_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0 && Bimg > 0 && B % Bimg == 0, "smooth_loss: flow batch %d must be a multiple of image batch %d", B, Bimg);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -235,7 +490,8 @@ int fill_smooth(SmoothParams& P, const uof_smooth_level* levels, int nlevels, in
     W[l] = levels[l].W;
   }
   P.Bimg = Bimg;
-  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, 1, blocks_per_sm, kWarpsPerBlock) > 0, "smooth_loss: problem too large");
+  UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, 1, blocks_per_sm, kWarpsPerBlock, quad ? 4 : 1, quad ? 4 : -1) > 0,
+              "smooth_loss: problem too large");
   return UOF_OK;
 }
 
@@ -421,10 +677,15 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
   UOF_REQUIRE(sums && loss, "smooth_loss_fwd: null output");
   SmoothParams P;
   static const int occ = resident_blocks(smooth_fwd_kernel, kWarpsPerBlock * 32);
-  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false, occ)) return rc;
+  static const int occ_quad = resident_blocks(smooth_fwd_quad_kernel, kWarpsPerBlock * 32);
+  const bool quad = smooth_quad_ok(levels, nlevels, false);
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false, quad ? occ_quad : occ, quad)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
-  smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  if (quad)
+    smooth_fwd_quad_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+  else
+    smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   smooth_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
   count_launch(2);
   return check_launch("smooth_loss_fwd");
@@ -435,9 +696,15 @@ extern "C" int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, 
   UOF_REQUIRE(g_loss, "smooth_loss_bwd: null input");
   SmoothParams P;
   static const int occ = resident_blocks(smooth_bwd_kernel, kWarpsPerBlock * 32);
-  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 2, true, occ)) return rc;
-  smooth_bwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
-                      static_cast<cudaStream_t>(stream_)>>>(P, g_loss);
+  static const int occ_quad = resident_blocks(smooth_bwd_quad_kernel, kWarpsPerBlock * 32);
+  const bool quad = smooth_quad_ok(levels, nlevels, true);
+  if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 2, true, quad ? occ_quad : occ, quad)) return rc;
+  if (quad)
+    smooth_bwd_quad_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                             static_cast<cudaStream_t>(stream_)>>>(P, g_loss);
+  else
+    smooth_bwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                        static_cast<cudaStream_t>(stream_)>>>(P, g_loss);
   count_launch();
   return check_launch("smooth_loss_bwd");
 }

@@ -39,11 +39,13 @@ __device__ __forceinline__ bool locate_strip(const StripTable& T, int gw, int la
 // The launch runs `grid_mult` x ceil(warps / warps_per_block) blocks on 148 * blocks_per_sm resident slots; the strip
 // height is the one that minimises (number of waves) x (rows + 2*halo), i.e. whole waves with the least halo
 // re-computation (a 1.3-wave launch costs as much as a 2-wave one).  Returns the number of warps, or -1 on overflow.
+// `halo` is the row halo (and the column halo unless `col_halo` >= 0 is given: the quad kernels use whole lanes).
 inline long long build_strip_table(StripTable& T, const int* H, const int* W, int nlevels, int B, int halo,
-                                   int grid_mult = 1, int blocks_per_sm = 4, int warps_per_block = 4, int ppl = 1) {
+                                   int grid_mult = 1, int blocks_per_sm = 4, int warps_per_block = 4, int ppl = 1,
+                                   int col_halo = -1) {
   T.nlevels = nlevels;
   T.B = B;
-  const int outw = 32 * ppl - 2 * halo;
+  const int outw = 32 * ppl - 2 * (col_halo >= 0 ? col_halo : halo);
   const long long slots = (long long)kNumSMs * (blocks_per_sm > 0 ? blocks_per_sm : 1);
   int best_rows = 8;
   double best_cost = 1e300;

@@ -38,17 +38,35 @@ struct RunCoord {
   bool live;
 };
 
-// Grid = (runs per row, ceil(H / kWarps), B * nchunk): block (run, row group, b * nchunk + chunk), warp = row within
-// the group.  No per-thread division: the first version decoded a linear 64-bit warp index with three long-long
-// div/mod pairs, ~150 of the ~580 instructions a warp executed for an image warp (ncu source page, round 2).
-__device__ __forceinline__ RunCoord locate_run(int H, int nchunk, int run_px) {
+// Warp -> (batch, channel chunk, row, run of 32*PXT pixels) without 64-bit arithmetic: blockIdx.z = b * nchunk + chunk,
+// and within that plane either
+//   linear map (runs_per_row > 0): warp w = blockIdx.x * kWarps + warp id covers run w % runs_per_row of row
+//     w / runs_per_row, so a block reads 4 consecutive runs of one row (one 32-bit division); or
+//   row map (runs_per_row == 0): grid (runs, ceil(H / kWarps)), a block covers the same run of 4 consecutive rows.
+// The first version decoded a linear 64-bit index with three long-long div/mod pairs: ~150 of the ~580 instructions a
+// warp executed for an image warp (ncu source page, round 2).
+__device__ __forceinline__ RunCoord locate_run(int H, int nchunk, int run_px, int runs_per_row) {
   RunCoord rc;
-  rc.y = (int)blockIdx.y * kWarps + (int)(threadIdx.x >> 5);
+  const unsigned warp = threadIdx.x >> 5;
+  unsigned run;
+  if (runs_per_row > 0) {
+    const unsigned w = blockIdx.x * kWarps + warp;
+    rc.y = (int)(w / (unsigned)runs_per_row);
+    run = w - (unsigned)rc.y * (unsigned)runs_per_row;
+  } else {
+    run = blockIdx.x;
+    rc.y = (int)(blockIdx.y * kWarps + warp);
+  }
   rc.b = (int)(blockIdx.z / (unsigned)nchunk);           // block-uniform
   rc.chunk = (int)blockIdx.z - rc.b * nchunk;
-  rc.x0 = (int)blockIdx.x * run_px;
+  rc.x0 = (int)run * run_px;
   rc.live = rc.y < H;
   return rc;
+}
+
+// grid for the mapping above; `row_map` selects the second form
+dim3 run_grid(int B, int nchunk, int H, int runs, bool row_map) {
+  return row_map ? dim3(runs, ceil_div(H, kWarps), B * nchunk) : dim3(ceil_div(H * runs, kWarps), 1, B * nchunk);
 }
 
 // ---------------------------------------------------------------------------------- NCHW fwd
@@ -57,7 +75,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out, int B, int C,
                      int H, int W, int nchunk, int runs_per_row, int use_mask, int align_corners) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run(H, nchunk, 32 * PXT);
+  const RunCoord rc = locate_run(H, nchunk, 32 * PXT, runs_per_row);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const float* fb = flow + (size_t)rc.b * 2 * plane + (size_t)rc.y * W;
@@ -87,19 +105,33 @@ warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow
   const int c0 = rc.chunk * cch, c1 = min(C, c0 + cch);
   const float* xp = x + ((size_t)rc.b * C + c0) * plane;
   float* op = out + ((size_t)rc.b * C + c0) * plane + (size_t)rc.y * W + rc.x0 + lane;
-#pragma unroll UNR
-  for (int c = c0; c < c1; ++c, xp += plane, op += plane) {
-    float v[PXT][4];
+  // UNR channels per batch: all 4 * PXT * UNR gathers of a batch are issued before the first use (with a plain
+  // `#pragma unroll` over channels ptxas kept the per-channel load -> blend -> store order, 4 * PXT loads in flight)
+  for (int c = c0; c < c1; c += UNR, xp += (size_t)UNR * plane, op += (size_t)UNR * plane) {
+    float v[UNR][PXT][4];
 #pragma unroll
-    for (int k = 0; k < PXT; ++k) {      // clamped offsets are always valid addresses
-      v[k][0] = __ldg(xp + fp[k].o00);
-      v[k][1] = __ldg(xp + fp[k].o01);
-      v[k][2] = __ldg(xp + fp[k].o10);
-      v[k][3] = __ldg(xp + fp[k].o11);
+    for (int cb = 0; cb < UNR; ++cb) {
+      if (c + cb < c1) {
+        const float* xc = xp + (size_t)cb * plane;
+#pragma unroll
+        for (int k = 0; k < PXT; ++k) {      // clamped offsets are always valid addresses
+          v[cb][k][0] = __ldg(xc + fp[k].o00);
+          v[cb][k][1] = __ldg(xc + fp[k].o01);
+          v[cb][k][2] = __ldg(xc + fp[k].o10);
+          v[cb][k][3] = __ldg(xc + fp[k].o11);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < PXT; ++k)
-      if (ok[k]) op[32 * k] = fmaf(v[k][3], fp[k].w11, fmaf(v[k][2], fp[k].w10, fmaf(v[k][1], fp[k].w01, v[k][0] * fp[k].w00)));
+    for (int cb = 0; cb < UNR; ++cb) {
+      if (c + cb < c1) {
+#pragma unroll
+        for (int k = 0; k < PXT; ++k)
+          if (ok[k])
+            op[(size_t)cb * plane + 32 * k] =
+                fmaf(v[cb][k][3], fp[k].w11, fmaf(v[cb][k][2], fp[k].w10, fmaf(v[cb][k][1], fp[k].w01, v[cb][k][0] * fp[k].w00)));
+      }
+    }
   }
 }
 
@@ -111,7 +143,7 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
                      float* __restrict__ gx, float* __restrict__ gflow, int B, int C, int H, int W, int nchunk,
                      int runs_per_row, int use_mask, int align_corners, float sx, float sy) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run(H, nchunk, 32 * PXT);
+  const RunCoord rc = locate_run(H, nchunk, 32 * PXT, runs_per_row);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const size_t row = (size_t)rc.y * W;
@@ -164,48 +196,58 @@ warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x
   float gix[PXT], giy[PXT];
 #pragma unroll
   for (int k = 0; k < PXT; ++k) gix[k] = giy[k] = 0.0f;
-#pragma unroll UNR
-  for (int c = c0; c < c1; ++c, xp += plane, gp += plane) {
-    float g[PXT], v[PXT][4];
+  // UNR channels per batch, all loads of a batch issued before the first use (see the forward kernel)
+  for (int c = c0; c < c1; c += UNR, xp += (size_t)UNR * plane, gp += (size_t)UNR * plane) {
+    float g[UNR][PXT], v[UNR][PXT][4];
 #pragma unroll
-    for (int k = 0; k < PXT; ++k) g[k] = ok[k] ? __ldg(gp + 32 * k) : 0.0f;
+    for (int cb = 0; cb < UNR; ++cb) {
+      if (c + cb < c1) {
+        const float* xc = xp + (size_t)cb * plane;
 #pragma unroll
-    for (int k = 0; k < PXT; ++k) {
-      v[k][0] = __ldg(xp + fp[k].o00);
-      v[k][1] = __ldg(xp + fp[k].o01);
-      v[k][2] = __ldg(xp + fp[k].o10);
-      v[k][3] = __ldg(xp + fp[k].o11);
+        for (int k = 0; k < PXT; ++k) g[cb][k] = ok[k] ? __ldg(gp + (size_t)cb * plane + 32 * k) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < PXT; ++k) {
+          v[cb][k][0] = __ldg(xc + fp[k].o00);
+          v[cb][k][1] = __ldg(xc + fp[k].o01);
+          v[cb][k][2] = __ldg(xc + fp[k].o10);
+          v[cb][k][3] = __ldg(xc + fp[k].o11);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < PXT; ++k) {
-      const float gm = g[k] * msk[k];
-      const float v00 = (inb[k] & 1u) ? v[k][0] : 0.0f, v01 = (inb[k] & 2u) ? v[k][1] : 0.0f;
-      const float v10 = (inb[k] & 4u) ? v[k][2] : 0.0f, v11 = (inb[k] & 8u) ? v[k][3] : 0.0f;
-      // d out / d ix and d out / d iy of the bilinear interpolant
-      gix[k] = fmaf(gm, (v01 - v00) * uy[k] + (v11 - v10) * ty[k], gix[k]);
-      giy[k] = fmaf(gm, (v10 - v00) * ux[k] + (v11 - v01) * tx[k], giy[k]);
-      if (NEED_GX) {
-        float* q = gxp + (size_t)(c - c0) * plane;
-        float c00 = gm * fp[k].w00, c01 = gm * fp[k].w01, c10 = gm * fp[k].w10, c11 = gm * fp[k].w11;
-        if (PXT == 1) {
-          // warp-aggregated scatter: the right-hand corners of lane-1 are this lane's left-hand corners whenever the
-          // two footprints sit side by side (`take`); add them here and let lane-1 skip its two REDs (`taken`)
-          const float n01 = __shfl_up_sync(kFullMask, c01, 1), n11 = __shfl_up_sync(kFullMask, c11, 1);
-          if (take) {
-            c00 += n01;
-            c10 += n11;
-          }
-          if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
-          if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
-          if (!taken) {
+    for (int cb = 0; cb < UNR; ++cb) {
+      if (c + cb >= c1) continue;
+#pragma unroll
+      for (int k = 0; k < PXT; ++k) {
+        const float gm = g[cb][k] * msk[k];
+        const float v00 = (inb[k] & 1u) ? v[cb][k][0] : 0.0f, v01 = (inb[k] & 2u) ? v[cb][k][1] : 0.0f;
+        const float v10 = (inb[k] & 4u) ? v[cb][k][2] : 0.0f, v11 = (inb[k] & 8u) ? v[cb][k][3] : 0.0f;
+        // d out / d ix and d out / d iy of the bilinear interpolant
+        gix[k] = fmaf(gm, (v01 - v00) * uy[k] + (v11 - v10) * ty[k], gix[k]);
+        giy[k] = fmaf(gm, (v10 - v00) * ux[k] + (v11 - v01) * tx[k], giy[k]);
+        if (NEED_GX) {
+          float* q = gxp + (size_t)(c + cb - c0) * plane;
+          float c00 = gm * fp[k].w00, c01 = gm * fp[k].w01, c10 = gm * fp[k].w10, c11 = gm * fp[k].w11;
+          if (PXT == 1) {
+            // warp-aggregated scatter: the right-hand corners of lane-1 are this lane's left-hand corners whenever the
+            // two footprints sit side by side (`take`); add them here and let lane-1 skip its two REDs (`taken`)
+            const float n01 = __shfl_up_sync(kFullMask, c01, 1), n11 = __shfl_up_sync(kFullMask, c11, 1);
+            if (take) {
+              c00 += n01;
+              c10 += n11;
+            }
+            if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
+            if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
+            if (!taken) {
+              if (inb[k] & 2u) atomicAdd(q + fp[k].o01, c01);
+              if (inb[k] & 8u) atomicAdd(q + fp[k].o11, c11);
+            }
+          } else {
+            if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
             if (inb[k] & 2u) atomicAdd(q + fp[k].o01, c01);
+            if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
             if (inb[k] & 8u) atomicAdd(q + fp[k].o11, c11);
           }
-        } else {
-          if (inb[k] & 1u) atomicAdd(q + fp[k].o00, c00);
-          if (inb[k] & 2u) atomicAdd(q + fp[k].o01, c01);
-          if (inb[k] & 4u) atomicAdd(q + fp[k].o10, c10);
-          if (inb[k] & 8u) atomicAdd(q + fp[k].o11, c11);
         }
       }
     }
@@ -354,9 +396,14 @@ extern "C" int uof_warp_fwd(const float* x, const float* flow, float* out, int B
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, false), runs = ceil_div(W, 32 * pxt);
     UOF_REQUIRE((long long)B * nchunk <= 65535 && ceil_div(H, kWarps) <= 65535, "warp_fwd: grid too large (B*chunks=%lld)", (long long)B * nchunk);
-    const dim3 blocks(runs, ceil_div(H, kWarps), B * nchunk);
-#define UOF_FWD(P, U) warp_fwd_nchw_kernel<P, U><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, runs, use_mask, align_corners)
-    static const int unr = env_int("UOF_WARP_UNROLL");
+    // measured (profiles/r2_warp_map.txt): the forward kernel is faster when a block reads 4 consecutive runs of one row
+    static const int fmap = env_int("UOF_WARP_FWD_ROWMAP");
+    const dim3 blocks = run_grid(B, nchunk, H, runs, fmap == 1);
+    const int rpr = fmap == 1 ? 0 : runs;
+#define UOF_FWD(P, U) warp_fwd_nchw_kernel<P, U><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, rpr, use_mask, align_corners)
+    // channels per load batch: 4 for feature maps (measured 30.4 -> 26.4 us at 16x32x64x208), 2 for 3-channel images
+    static const int unr_env = env_int("UOF_WARP_UNROLL");
+    const int unr = (unr_env == 2 || unr_env == 4) ? unr_env : (C >= 8 ? 4 : 2);
     if (pxt == 4) UOF_FWD(4, 2); else if (pxt == 2) { if (unr == 4) UOF_FWD(2, 4); else UOF_FWD(2, 2); } else { if (unr == 4) UOF_FWD(1, 4); else UOF_FWD(1, 2); }
 #undef UOF_FWD
   } else {
@@ -373,16 +420,19 @@ template <int PXT>
 static void launch_bwd_nchw(const float* gout, const float* x, const float* flow, float* gx, float* gflow, int B, int C,
                             int H, int W, int nchunk, int runs, int use_mask, int align_corners, float sx, float sy,
                             cudaStream_t stream) {
-  const dim3 blocks(runs, ceil_div(H, kWarps), B * nchunk);
-  static const int unr = env_int("UOF_WARP_UNROLL");
+  static const int bmap = env_int("UOF_WARP_BWD_LINMAP");
+  const dim3 blocks = run_grid(B, nchunk, H, runs, bmap != 1);
+  const int rpr = bmap != 1 ? 0 : runs;
+  static const int unr_env = env_int("UOF_WARP_UNROLL");
+  const int unr = (unr_env == 2 || unr_env == 4) ? unr_env : (C >= 8 ? 4 : 2);
 #define UOF_LAUNCH(GX, AT)                                                                                              \
   do {                                                                                                                  \
     if (unr == 4 && PXT == 1)                                                                                           \
       warp_bwd_nchw_kernel<PXT, GX, AT, (PXT == 1 ? 4 : 2)><<<blocks, kWarps * 32, 0, stream>>>(                         \
-          gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy);                         \
+          gout, x, flow, gx, gflow, B, C, H, W, nchunk, rpr, use_mask, align_corners, sx, sy);                          \
     else                                                                                                                \
       warp_bwd_nchw_kernel<PXT, GX, AT, 2><<<blocks, kWarps * 32, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W,    \
-                                                                               nchunk, runs, use_mask, align_corners,  \
+                                                                               nchunk, rpr, use_mask, align_corners,   \
                                                                                sx, sy);                                 \
   } while (0)
   if (gx) {
