@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--ddp', action='store_true',
+                    help='N > 1: eager DistributedDataParallel step instead of the graphed flat all-reduce step')
     ap.add_argument('--profile-step', action='store_true',
                     help='warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
@@ -282,7 +284,7 @@ def run_b200(args):
     torch.manual_seed(0)
     model = u.Model_flow(cfg).to(dev)
     net = model
-    if world > 1:
+    if world > 1 and (args.ddp or args.no_graph):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=8, broadcast_buffers=False)
     opt = T.make_optimizer(model, cfg.lr)
@@ -298,13 +300,15 @@ def run_b200(args):
     def eager_step(x):
         return T.train_step(net, opt, x, weights)
 
-    # One GPU: the whole iteration is captured into a CUDA graph (unopticalflow_b200.train.GraphedTrainStep, the
-    # package's public training-step API) and replayed.  N > 1 runs the same iteration eagerly under DDP/NCCL.
-    use_graph = (world == 1) and not args.no_graph
+    # The whole iteration is captured into a CUDA graph (unopticalflow_b200.train.GraphedTrainStep, the package's
+    # public training-step API) and replayed.  N > 1: gradients live in one flat buffer and are averaged by a single
+    # NCCL all-reduce captured in the same graph (train.FlatGradAllReduce); `--ddp` (or `--no-graph`) runs the
+    # iteration eagerly under DistributedDataParallel instead.
+    use_graph = not args.no_graph and not (world > 1 and args.ddp)
     launches_per_graph_step = 0
     if use_graph:
         n_before = _lib.launch_count()
-        graphed = T.GraphedTrainStep(model, resident[0], weights, cfg.lr, warmup=3)
+        graphed = T.GraphedTrainStep(model, resident[0], weights, cfg.lr, warmup=3, allreduce=world > 1)
         launches_per_graph_step = (_lib.launch_count() - n_before) // 4      # 3 eager warm-ups + 1 capture pass
         step = graphed
     else:
@@ -365,7 +369,7 @@ def run_b200(args):
     ms_step = timed(lambda i: step(resident[i % NBUF]), args.steps)
     launches = (_lib.launch_count() - n0) * world
     if use_graph:      # replayed kernels do not pass through the C ABI again: count what one captured step holds
-        launches = launches_per_graph_step * args.steps
+        launches = launches_per_graph_step * args.steps * world
     clocks = sampler.stop() if sampler else {}
 
     # ---- end to end: pinned host inputs -> H2D every step, loss read back every step ---------------
@@ -410,13 +414,16 @@ def run_b200(args):
             'config': {'workload': 'kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam), synthetic 256x832 triplets',
                        'img_hw': [H, W], 'batch_per_gpu': B, 'global_batch': B * world, 'frame_pairs_per_triplet': 2,
                        'triplets_per_s': round(B * world / (ms_step * 1e-3), 3),
-                       'parallelism': 'ddp%d' % world if world > 1 else 'single', 'tf32': False, 'cuda_graph': bool(use_graph),
+                       'parallelism': ('dp%d (one process per GPU, %s)' % (world, 'one flat NCCL all-reduce of the gradients inside the '
+                                       'CUDA graph' if use_graph else 'DistributedDataParallel, NCCL')) if world > 1 else 'single',
+                       'tf32': False, 'cuda_graph': bool(use_graph),
                        'l2': '%d distinct resident input batches (%.0f MB total > 126 MB L2) rotated; step working set is GBs'
                              % (NBUF, NBUF * in_bytes / 1e6)},
             'clocks': clocks,
             'e2e': {'value': round(fp_per_step / (ms_e2e * 1e-3), 3), 'unit': UNIT, 'ms_per_step': round(ms_e2e, 3),
                     'h2d_bytes_per_step': in_bytes * world, 'd2h_bytes_per_step': 4 * world,
-                    'api': ('unopticalflow_b200.train.GraphedTrainStep(Model_flow, pinned-host batch)' if use_graph else
+                    'api': ('unopticalflow_b200.train.GraphedTrainStep(Model_flow, pinned-host batch%s)'
+                            % (', allreduce=True' if world > 1 else '') if use_graph else
                             'unopticalflow_b200.train.train_step(DDP(Model_flow), Adam, pinned-host batch)')},
             'gpu_launches': int(launches),
             'own_kernels_ms_per_step': round(own_ms, 3),
@@ -441,7 +448,21 @@ def run_b200(args):
                                               'oracle port: fwd+bwd+Adam, %.2f s/step' % (B, s_per_step)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown: a CUDA graph that holds captured NCCL kernels must be released before the communicator, and a
+        # communicator teardown that still blocks (seen once at N=2: the JSON line was out, the process never exited)
+        # must not hang the launcher -- a daemon timer ends the process after a grace period.
+        import threading
+        sys.stdout.flush()
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        torch.cuda.synchronize()
+        if use_graph:
+            step.graph.reset()
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 def main():

@@ -32,10 +32,20 @@ def _worker(rank, world, port, out_dir):
     pack = ddp(x[rank:rank + 1])
     T.total_loss(pack, w).backward()
     grads = torch.cat([p.grad.flatten() for p in model.parameters()])
+    # the graph-capturable exchange (train.FlatGradAllReduce): same model, gradients in one flat buffer, one all-reduce
+    torch.manual_seed(0)
+    model2 = omodel.Model_flow(omodel.Cfg)
+    ex = T.FlatGradAllReduce(list(model2.parameters()))
+    for _ in range(2):                       # twice: zero() must clear what the previous step accumulated
+        ex.zero()
+        T.total_loss(model2(x[rank:rank + 1]), w).backward()
+        ex.allreduce()
+    assert all(p.grad.data_ptr() >= ex.flat.data_ptr() for p in model2.parameters()), 'grads must stay views of the flat buffer'
+    flat = ex.flat.clone()
     # max-over-ranks reduction used by bench.py for timing
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    torch.save({'grads': grads, 'tmax': t}, os.path.join(out_dir, 'rank%d.pt' % rank))
+    torch.save({'grads': grads, 'flat': flat, 'tmax': t}, os.path.join(out_dir, 'rank%d.pt' % rank))
     dist.destroy_process_group()
 
 
@@ -54,6 +64,10 @@ def test_ddp_gradients_equal_single_process(tmp_path):
     T.total_loss(model(x), T.generate_loss_weights_dict(T.KITTI_CFG)).backward()
     ref = torch.cat([p.grad.flatten() for p in model.parameters()])
     err = float((r0['grads'] - ref).norm() / ref.norm())
+    assert err < 1e-5, err
+    # flat-buffer exchange == DDP == single process
+    assert torch.equal(r0['flat'], r1['flat'])
+    err = float((r0['flat'] - ref).norm() / ref.norm())
     assert err < 1e-5, err
 
 
