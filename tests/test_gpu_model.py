@@ -51,20 +51,34 @@ def test_step_matches_oracle_and_reference_golden(U, tag, B, H, W):
     assert float((gv - rv).norm() / rv.norm()) <= REL_TOL
     gn = torch.stack([p.grad.norm() for p in m.parameters()]).cpu()
     assert_close(gn, g['grad_norms'], 2e-4, 'grad norms vs reference golden')
-    assert global_grad_err_vs_same_gpu_oracle(m, ref, x) <= REL_TOL
+    err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x)
+    assert err <= REL_TOL + noise, (err, noise)
 
 
 def global_grad_err_vs_same_gpu_oracle(m, ref, x, **loss_kw):
     """The CPU oracle and the CUDA path run different convolution back ends (mkldnn vs cuDNN), which alone moves parameter
     gradients by up to ~1e-4.  Running the oracle's op chain on the SAME GPU (same cuDNN convolutions, TF32 off) isolates the
-    hand-written kernels: relative L2 error of the whole gradient vector."""
+    hand-written kernels: relative L2 error of the whole gradient vector.
+
+    Returns (err, noise).  `noise` is the run-to-run spread of the two implementations themselves (each run twice on the
+    same input): both scatter with fp32 atomics (ATen's grid_sampler backward, our warp / cost-volume kernels), and the
+    smoothness loss back-propagates the SIGN of second differences that are pure rounding noise on the bilinearly
+    up-sampled flows, so a last-bit difference upstream flips whole gradient entries.  At 448x1024 that spread reaches
+    ~1e-4 by itself; the parity bar is applied to the error in excess of it."""
     import copy
     ref_gpu = copy.deepcopy(ref).cuda()
-    ref_gpu.zero_grad(set_to_none=True)
-    O.total_loss(ref_gpu(x.cuda()), **loss_kw).backward()
-    gv = torch.cat([p.grad.flatten() for p in m.parameters()])
-    rv = torch.cat([q.grad.flatten() for q in ref_gpu.parameters()])
-    return float((gv - rv).norm() / rv.norm())
+    xc = x.cuda()
+
+    def grad_of(model):
+        model.zero_grad(set_to_none=True)
+        O.total_loss(model(xc), **loss_kw).backward()
+        return torch.cat([p.grad.flatten() for p in model.parameters()]).clone()
+
+    gv, gv2 = grad_of(m), grad_of(m)
+    rv, rv2 = grad_of(ref_gpu), grad_of(ref_gpu)
+    n = float(rv.norm())
+    noise = float((gv - gv2).norm()) / n + float((rv - rv2).norm()) / n
+    return float((gv - rv).norm()) / n, noise
 
 
 def test_inference_flow_matches_oracle(U):
@@ -120,6 +134,29 @@ def test_graphed_train_step_matches_eager(U):
         le = float(T.train_step(m1, opt, xs[i % 3], w))
         lg = float(graphed(xs[i % 3]))
         assert abs(le - lg) <= 2e-4 * abs(le), (i, le, lg)
+
+
+def test_graphed_step_staged_inputs_and_flat_gradients(U):
+    """The two additions of the data-parallel step at world size 1: (a) gradients living in one flat buffer
+    (train.FlatGradAllReduce, the all-reduce is a no-op without a process group) and (b) the staged input pipeline
+    (stage(next) overlapping step()) must give the same loss trajectory as the plain graphed step fed directly."""
+    from unopticalflow_b200 import train as T
+    torch.manual_seed(0)
+    m1, m2 = U.Model_flow(T.KITTI_CFG).cuda(), U.Model_flow(T.KITTI_CFG).cuda()
+    m2.load_state_dict(m1.state_dict())
+    w = T.generate_loss_weights_dict(T.KITTI_CFG)
+    gen = torch.Generator().manual_seed(99)
+    host = [torch.rand(2, 3, 192, 128, generator=gen).pin_memory() for _ in range(3)]
+    direct = T.GraphedTrainStep(m1, host[0].cuda(), w, warmup=3)
+    staged = T.GraphedTrainStep(m2, host[0].cuda(), w, warmup=3, allreduce=True)
+    assert all(p.grad.data_ptr() >= staged.exchange.flat.data_ptr() for p in m2.parameters())
+    staged.stage(host[0])
+    for i in range(5):
+        ld = float(direct(host[i % 3]))
+        loss = staged()
+        staged.stage(host[(i + 1) % 3])
+        ls = float(loss)
+        assert abs(ld - ls) <= 2e-4 * abs(ld), (i, ld, ls)
 
 
 def test_occlusion_extras(U):
@@ -187,7 +224,9 @@ def test_config4_sintel_shape_step(U):
     gv = torch.cat([p.grad.flatten().cpu() for p in m.parameters()])
     rv = torch.cat([q.grad.flatten() for q in ref.parameters()])
     assert float((gv - rv).norm() / rv.norm()) <= 3e-4          # CPU (mkldnn) vs GPU (cuDNN) convolutions differ by ~1e-4
-    assert global_grad_err_vs_same_gpu_oracle(m, ref, x[:1], w_smooth=6.0) <= REL_TOL
+    err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x[:1], w_smooth=6.0)
+    assert err <= REL_TOL + noise, (err, noise)
+    print('sintel-shape gradient: err vs same-GPU oracle %.2e, run-to-run spread %.2e' % (err, noise))
     m.zero_grad(set_to_none=True)
     xc = x.cuda()
     p1 = m(xc)

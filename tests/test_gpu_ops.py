@@ -318,6 +318,36 @@ def test_photometric_backward_kernel_variants_agree(U):
 
 
 # --------------------------------------------------------------------------------------- a7/a8
+@pytest.mark.parametrize('B,H,W', [(1, 64, 256), (2, 48, 128)])
+def test_smooth_wide_piecewise_linear_flows(U, B, H, W):
+    """Quad-layout smoothness kernels (W % 4 == 0, several 120-column strips) on the flows the decoder actually produces:
+    bilinearly up-sampled, i.e. piecewise linear, so second differences are rounding noise over large areas and the
+    gradient is the SIGN of that noise -- the kernels must round like the reference (no FMA contraction).  Also covers the
+    backward pass with a flow batch of 2B against an image batch of B, as Model_flow.forward uses it."""
+    g = torch.Generator().manual_seed(H + W)
+    S = 3
+    imgs = O.img_pyramid(torch.rand(B, 3, H, W, generator=g), S)
+    lo = torch.randn(2 * B, 2, H // 8, W // 8, generator=g) * 3.0
+    flows = [torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)
+             for s in range(S)]
+    ct = torch.randn(2 * B, generator=g)
+    # The oracle's op chain is run ON THE GPU here: `flow / 20.0` is a true division in ATen's CPU kernel but a
+    # multiplication by 0.05f in its CUDA kernel (BinaryDivTrueKernel.cu, CPU-scalar divisor), and on these inputs the
+    # last bit decides the sign of the second difference.  The reference trains on the GPU, so that is the behaviour to
+    # match; the CPU oracle agrees on generic inputs (test_smooth_and_consis_vs_oracle).
+    rflows = [f.clone().cuda().requires_grad_(True) for f in flows]
+    rimgs = [i.cuda() for i in imgs]
+    ref = torch.cat((O.loss_flow_smooth([f[:B] for f in rflows], rimgs, S), O.loss_flow_smooth([f[B:] for f in rflows], rimgs, S)))
+    ref_g = torch.autograd.grad((ref * ct.cuda()).sum(), rflows)
+    cf = [gpu(f, True) for f in flows]
+    got = U.ops.flow_smooth_loss(cf, [i.cuda() for i in imgs], S)
+    got_g = torch.autograd.grad((got * ct.cuda()).sum(), cf)
+    assert_close(got, ref, REL_TOL, 'smooth loss, 2B flows vs B images')
+    for a, b in zip(got_g, ref_g):
+        assert float(b.abs().max()) > 0
+        assert_close(a, b, REL_TOL, 'd smooth / d flow on piecewise-linear flows')
+
+
 @pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 24, 66), (2, 8, 12)])
 def test_smooth_and_consis_vs_oracle(U, B, H, W):
     g = torch.Generator().manual_seed(B + H + W)
