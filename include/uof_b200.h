@@ -83,7 +83,12 @@ typedef struct {
   float* gwarped_r;
   int H, W;
 } uof_photo_level;
-/* sums: (nlevels,B,6) workspace, zero-filled here, then
+/* Reduction workspaces of the fused loss entry points (photo, smooth, consis): `sums` holds nlevels*B*K partial sums
+ * followed by UOF_SUMS_EXTRA floats reserved for the kernels (smooth_loss_fwd keeps a block counter there: the last
+ * block to finish forms the (B) losses, so it needs no separate finalize launch).  Allocate nlevels*B*K + UOF_SUMS_EXTRA floats; the backward entry
+ * points read only the first nlevels*B*K. */
+#define UOF_SUMS_EXTRA 1
+/* sums: (nlevels,B,6) + UOF_SUMS_EXTRA workspace, zero-filled here, then
  *   [0]=sum d_l*w_l [1]=sum w_l [2]=sum d_r*w_r [3]=sum w_r [4]=sum ssim_term_l [5]=sum ssim_term_r
  * loss_pixel, loss_ssim: (B) out, summed over levels and both directions. */
 int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B,
@@ -128,7 +133,7 @@ typedef struct {
   int H, W;
 } uof_smooth_level;
 int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
-                        float* sums /* (nlevels,B,2) */, float* loss /* (B) */, uof_stream_t stream);
+                        float* sums /* (nlevels,B,2) + UOF_SUMS_EXTRA */, float* loss /* (B) */, uof_stream_t stream);
 int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
                         const float* g_loss, uof_stream_t stream);
 
@@ -142,7 +147,7 @@ typedef struct {
   int H, W;
 } uof_consis_level;
 int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, int B,
-                        float* sums /* (nlevels,B,2) */, float* loss /* (B) */, uof_stream_t stream);
+                        float* sums /* (nlevels,B,2) + UOF_SUMS_EXTRA */, float* loss /* (B) */, uof_stream_t stream);
 int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, const float* sums,
                         const float* g_loss, uof_stream_t stream);
 

@@ -294,7 +294,7 @@ def test_photometric_backward_kernel_variants_agree(U):
         wr = [torch.rand(B, 3, H >> s, W >> s, generator=g).cuda() for s in range(S)]
         wtl = [torch.empty(B, 1, H >> s, W >> s, device='cuda') for s in range(S)]
         wtr = [torch.empty(B, 1, H >> s, W >> s, device='cuda') for s in range(S)]
-        sums, lp, ls = torch.empty(S, B, 6, device='cuda'), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+        sums, lp, ls = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, device='cuda'), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
         gp, gs = torch.rand(B, generator=g).cuda(), torch.rand(B, generator=g).cuda()
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: ctypes.c_void_p(t.data_ptr())

@@ -15,6 +15,9 @@ c_float_p = ctypes.c_void_p   # device pointers travel as integers
 MAX_LEVELS = 4
 
 
+SUMS_EXTRA = 1      # include/uof_b200.h UOF_SUMS_EXTRA: floats appended to every fused-loss `sums` workspace
+
+
 class PhotoLevel(ctypes.Structure):
     _fields_ = [('img', ctypes.c_void_p), ('warped_l', ctypes.c_void_p), ('warped_r', ctypes.c_void_p),
                 ('weight_l', ctypes.c_void_p), ('weight_r', ctypes.c_void_p),

@@ -74,6 +74,20 @@ __device__ __forceinline__ void block_accumulate(const float (&v)[K], float* dst
   }
 }
 
+// "Last block" epilogue: call after block_accumulate (every thread of the block).  Returns true in exactly one block
+// of the launch -- the one whose counter increment arrives last -- after which every block's REDs are visible, so
+// that block can form the final per-sample losses from the sums (read them with __ldcg).  Saves the separate
+// finalize launch (~5 us of launch + dependent-load latency for a one-block kernel).
+__device__ __forceinline__ bool last_block_done(unsigned* counter) {
+  __shared__ bool is_last;
+  __threadfence();                 // this thread's REDs are ordered before the counter increment below
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
 // ---- streaming loads/stores -------------------------------------------------------------------
 __device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 

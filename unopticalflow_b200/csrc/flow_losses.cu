@@ -23,6 +23,8 @@ struct SmoothParams {
   int Bimg;
 };
 
+__device__ void smooth_finalize(const SmoothParams& P, const float* sums, float* loss);
+
 __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
 
 // second difference (hi - mid) - (mid - lo) with the reference's roundings (model_flow_paper.py:153-155 applied twice)
@@ -65,7 +67,7 @@ __device__ __forceinline__ void take_row(const float* ring, int slot, float* v) 
 
 // --------------------------------------------------------------------------------- smooth fwd
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums) {
+smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums, float* __restrict__ loss) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   Strip sc;
@@ -128,19 +130,20 @@ smooth_fwd_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ su
   }
   const float acc[2] = {warp_sum(sum_x), warp_sum(sum_y)};
   block_accumulate<2, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 2 : nullptr);
+  if (last_block_done(reinterpret_cast<unsigned*>(sums + (size_t)P.T.nlevels * P.T.B * 2))) smooth_finalize(P, sums, loss);
 }
 
-__global__ void smooth_finalize_kernel(const __grid_constant__ SmoothParams P, const float* __restrict__ sums,
-                                       float* __restrict__ loss) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.T.B) return;
-  float acc = 0.0f;
-  for (int l = 0; l < P.T.nlevels; ++l) {
-    const float H = (float)P.lv[l].H, W = (float)P.lv[l].W;
-    const float* s = sums + ((size_t)l * P.T.B + b) * 2;
-    acc += (s[0] / (2.0f * H * (W - 2.0f)) + s[1] / (2.0f * (H - 2.0f) * W)) / 2.0f;   // :165-166
+// Runs in the last block of the forward launch (last_block_done).
+__device__ void smooth_finalize(const SmoothParams& P, const float* sums, float* loss) {
+  for (int b = threadIdx.x; b < P.T.B; b += blockDim.x) {
+    float acc = 0.0f;
+    for (int l = 0; l < P.T.nlevels; ++l) {
+      const float H = (float)P.lv[l].H, W = (float)P.lv[l].W;
+      const float* s = sums + ((size_t)l * P.T.B + b) * 2;
+      acc += (__ldcg(s) / (2.0f * H * (W - 2.0f)) + __ldcg(s + 1) / (2.0f * (H - 2.0f) * W)) / 2.0f;   // :165-166
+    }
+    loss[b] = acc;
   }
-  loss[b] = acc;
 }
 
 // --------------------------------------------------------------------------------- smooth bwd
@@ -283,7 +286,7 @@ __device__ __forceinline__ float edge_l1(const float* a, const float* b) {
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-smooth_fwd_quad_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums) {
+smooth_fwd_quad_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums, float* __restrict__ loss) {
   __shared__ float4 ring_s[kWarpsPerBlock][kQDepth * kRowVals * 32];
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -361,6 +364,7 @@ smooth_fwd_quad_kernel(const __grid_constant__ SmoothParams P, float* __restrict
   }
   const float acc[2] = {warp_sum(sum_x), warp_sum(sum_y)};
   block_accumulate<2, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 2 : nullptr);
+  if (last_block_done(reinterpret_cast<unsigned*>(sums + (size_t)P.T.nlevels * P.T.B * 2))) smooth_finalize(P, sums, loss);
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -502,8 +506,10 @@ struct ConsisParams {
   int warps_per_sample[UOF_MAX_LEVELS];
   int nlevels, B;
   int vec4;          // every plane is a multiple of 4 pixels and every pointer 16-byte aligned
+  int px_per_warp;   // pixels owned by a warp: kConsisPxPerWarp (backward) or kConsisFwdChunks times that (forward)
 };
 constexpr int kConsisPxPerWarp = 32 * 8;
+constexpr int kConsisFwdChunks = 1;      // measured: 4 chunks per warp (4x fewer blocks, barriers, REDs) is not faster (19.0 vs 18.5 us)
 
 __device__ __forceinline__ bool locate_chunk(const ConsisParams& P, int gw, int& level, int& b, int& px0) {
   if (gw >= P.warp_begin[P.nlevels]) return false;
@@ -512,7 +518,7 @@ __device__ __forceinline__ bool locate_chunk(const ConsisParams& P, int gw, int&
   const int local = gw - P.warp_begin[l];
   level = l;
   b = local / P.warps_per_sample[l];
-  px0 = (local % P.warps_per_sample[l]) * kConsisPxPerWarp;
+  px0 = (local % P.warps_per_sample[l]) * P.px_per_warp;
   return true;
 }
 
@@ -544,45 +550,51 @@ consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ su
   const float* fb = L.flow_bwd + (size_t)b * 2 * plane;
   const float* wf = L.weight_fwd + (size_t)b * plane;
   constexpr int NIT = kConsisPxPerWarp / (32 * VEC);
-  float ax[NIT][VEC], ay[NIT][VEC], bx[NIT][VEC], by[NIT][VEC], w[NIT][VEC];
   const int plane_live = live_warp ? plane : 0;      // idle warps load nothing and contribute zeros
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int p = px0 + (it * 32 + lane) * VEC;
-    consis_load<VEC>(ff, p, plane_live, ax[it]);
-    consis_load<VEC>(ff + plane, p, plane_live, ay[it]);
-    consis_load<VEC>(fb, p, plane_live, bx[it]);
-    consis_load<VEC>(fb + plane, p, plane_live, by[it]);
-    consis_load<VEC>(wf, p, plane_live, w[it]);
-  }
   float num = 0.0f, den = 0.0f;
+  // a warp walks kConsisFwdChunks chunks of 256 pixels
+  for (int ch = 0; ch < kConsisFwdChunks; ++ch, px0 += kConsisPxPerWarp) {
+    if (px0 >= plane_live) break;
+    float ax[NIT][VEC], ay[NIT][VEC], bx[NIT][VEC], by[NIT][VEC], w[NIT][VEC];
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const bool live = px0 + (it * 32 + lane) * VEC < plane_live;
+    for (int it = 0; it < NIT; ++it) {
+      const int p = px0 + (it * 32 + lane) * VEC;
+      consis_load<VEC>(ff, p, plane_live, ax[it]);
+      consis_load<VEC>(ff + plane, p, plane_live, ay[it]);
+      consis_load<VEC>(fb, p, plane_live, bx[it]);
+      consis_load<VEC>(fb + plane, p, plane_live, by[it]);
+      consis_load<VEC>(wf, p, plane_live, w[it]);
+    }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float occ = live ? 1.0f - w[it][v] : 0.0f;                                               // :187
-      const float ia = __fdividef(1.0f, sqrtf(fmaf(ax[it][v], ax[it][v], ay[it][v] * ay[it][v])) + kEps);   // :49
-      const float ib = __fdividef(1.0f, sqrtf(fmaf(bx[it][v], bx[it][v], by[it][v] * by[it][v])) + kEps);
-      num = fmaf(fabsf(fmaf(ax[it][v], ia, bx[it][v] * ib)) + fabsf(fmaf(ay[it][v], ia, by[it][v] * ib)), occ, num);   // :191
-      den += occ;
+    for (int it = 0; it < NIT; ++it) {
+      const bool live = px0 + (it * 32 + lane) * VEC < plane_live;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float occ = live ? 1.0f - w[it][v] : 0.0f;                                               // :187
+        const float ia = __fdividef(1.0f, sqrtf(fmaf(ax[it][v], ax[it][v], ay[it][v] * ay[it][v])) + kEps);   // :49
+        const float ib = __fdividef(1.0f, sqrtf(fmaf(bx[it][v], bx[it][v], by[it][v] * by[it][v])) + kEps);
+        num = fmaf(fabsf(fmaf(ax[it][v], ia, bx[it][v] * ib)) + fabsf(fmaf(ay[it][v], ia, by[it][v] * ib)), occ, num);   // :191
+        den += occ;
+      }
     }
   }
   const float acc[2] = {warp_sum(num), warp_sum(den)};
   block_accumulate<2, kConsisFwdWarps>(acc, live_warp ? sums + ((size_t)level * P.B + b) * 2 : nullptr);
 }
 
+// Separate one-block launch (folding it into the forward kernel like smooth_fwd does brought nothing here: 18.5 -> 19.1 us,
+// the block counter is one more same-address atomic for each of the ~1100 short-lived blocks).
 __global__ void consis_finalize_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums,
                                        float* __restrict__ loss) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.B) return;
-  float acc = 0.0f;
-  for (int l = 0; l < P.nlevels; ++l) {
-    const float n = (float)P.lv[l].H * (float)P.lv[l].W;
-    const float* s = sums + ((size_t)l * P.B + b) * 2;
-    acc += (s[0] / (2.0f * n)) / (s[1] / n + kEps);   // :189-192
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.B; b += gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    for (int l = 0; l < P.nlevels; ++l) {
+      const float n = (float)P.lv[l].H * (float)P.lv[l].W;
+      const float* s = sums + ((size_t)l * P.B + b) * 2;
+      acc += (__ldcg(s) / (2.0f * n)) / (__ldcg(s + 1) / n + kEps);   // :189-192
+    }
+    loss[b] = acc;
   }
-  loss[b] = acc;
 }
 
 template <int VEC>
@@ -640,6 +652,7 @@ consis_bwd_kernel(const __grid_constant__ ConsisParams P, const float* __restric
 }
 
 int fill_consis(ConsisParams& P, const uof_consis_level* levels, int nlevels, int B, bool bwd) {
+  P.px_per_warp = bwd ? kConsisPxPerWarp : kConsisPxPerWarp * kConsisFwdChunks;
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "consis_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0, "consis_loss: bad batch %d", B);
   long long total = 0;
@@ -649,7 +662,7 @@ int fill_consis(ConsisParams& P, const uof_consis_level* levels, int nlevels, in
     if (bwd) UOF_REQUIRE(L.gflow_fwd, "consis_loss_bwd: level %d has no gradient buffer", l);
     UOF_REQUIRE((long long)L.H * L.W < (1ll << 30), "consis_loss: level %d too large", l);
     P.lv[l] = L;
-    P.warps_per_sample[l] = ceil_div(L.H * L.W, kConsisPxPerWarp);
+    P.warps_per_sample[l] = ceil_div(L.H * L.W, P.px_per_warp);
     P.warp_begin[l] = (int)total;
     total += (long long)P.warps_per_sample[l] * B;
     UOF_REQUIRE(total < (1ll << 30), "consis_loss: problem too large");
@@ -681,13 +694,12 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
   const bool quad = smooth_quad_ok(levels, nlevels, false);
   if (int rc = fill_smooth(P, levels, nlevels, B, Bimg, 1, false, quad ? occ_quad : occ, quad)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
+  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 2 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   if (quad)
-    smooth_fwd_quad_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+    smooth_fwd_quad_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums, loss);
   else
-    smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
-  smooth_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
-  count_launch(2);
+    smooth_fwd_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(P, sums, loss);
+  count_launch();
   return check_launch("smooth_loss_fwd");
 }
 
@@ -715,7 +727,7 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
   ConsisParams P;
   if (int rc = fill_consis(P, levels, nlevels, B, false)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 2 * sizeof(float), stream));
+  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 2 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   if (P.vec4)
     consis_fwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kConsisFwdWarps), kConsisFwdWarps * 32, 0, stream>>>(P, sums);
   else

@@ -187,21 +187,25 @@ photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__
   block_accumulate<6, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 6 : nullptr);
 }
 
-// loss_pixel[b] = sum_l sum_d mean(d*w)/(mean(w)+eps);  loss_ssim[b] likewise (model_flow_paper.py:94-98,141-147)
+// loss_pixel[b] = sum_l sum_d mean(d*w)/(mean(w)+eps);  loss_ssim[b] likewise (model_flow_paper.py:94-98,141-147).
+// A separate one-block launch: folding it into the forward kernel ("last block" pattern, as smooth_fwd does) was measured
+// SLOWER here (59.7 -> 69.6 us): the per-block __threadfence has to drain the block's weight-map stores and the counter
+// is one more same-address atomic per block.
 __global__ void photo_loss_finalize_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
                                            float* __restrict__ loss_pixel, float* __restrict__ loss_ssim) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.T.B) return;
-  float lp = 0.0f, ls = 0.0f;
-  for (int l = 0; l < P.T.nlevels; ++l) {
-    const float n = (float)P.lv[l].H * (float)P.lv[l].W;
-    const float* s = sums + ((size_t)l * P.T.B + b) * 6;
-    // reference order: forward/right term first, then backward/left (:241-245)
-    lp += (s[2] / n) / (s[3] / n + kEps) + (s[0] / n) / (s[1] / n + kEps);
-    ls += (s[5] / (3.0f * n)) / (s[3] / n + kEps) + (s[4] / (3.0f * n)) / (s[1] / n + kEps);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.T.B; b += gridDim.x * blockDim.x) {
+    float lp = 0.0f, ls = 0.0f;
+    for (int l = 0; l < P.T.nlevels; ++l) {
+      const float n = (float)P.lv[l].H * (float)P.lv[l].W;
+      const float* s = sums + ((size_t)l * P.T.B + b) * 6;
+      const float s0 = __ldcg(s), s1 = __ldcg(s + 1), s2 = __ldcg(s + 2), s3 = __ldcg(s + 3), s4 = __ldcg(s + 4), s5 = __ldcg(s + 5);
+      // reference order: forward/right term first, then backward/left (:241-245)
+      lp += (s2 / n) / (s3 / n + kEps) + (s0 / n) / (s1 / n + kEps);
+      ls += (s5 / (3.0f * n)) / (s3 / n + kEps) + (s4 / (3.0f * n)) / (s1 / n + kEps);
+    }
+    loss_pixel[b] = lp;
+    loss_ssim[b] = ls;
   }
-  loss_pixel[b] = lp;
-  loss_ssim[b] = ls;
 }
 
 // ------------------------------------------------------------------------------------- backward
@@ -611,7 +615,7 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
   static const int occ = resident_blocks(photo_loss_fwd_kernel, kWarpsPerBlock * 32);
   if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  UOF_CUDA(cudaMemsetAsync(sums, 0, (size_t)nlevels * B * 6 * sizeof(float), stream));
+  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
   photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);

@@ -38,27 +38,31 @@ struct RunCoord {
   bool live;
 };
 
-// Warp -> (batch, channel chunk, row, run of 32*PXT pixels) without 64-bit arithmetic: blockIdx.z = b * nchunk + chunk,
-// and within that plane either
-//   linear map (runs_per_row > 0): warp w = blockIdx.x * kWarps + warp id covers run w % runs_per_row of row
-//     w / runs_per_row, so a block reads 4 consecutive runs of one row (one 32-bit division); or
-//   row map (runs_per_row == 0): grid (runs, ceil(H / kWarps)), a block covers the same run of 4 consecutive rows.
+// Warp -> (batch, channel chunk, row, run of 32*PXT pixels) without any division: grid = (x, nchunk, B) and within
+// the (b, chunk) plane either
+//   linear map (run_magic != 0): warp w = blockIdx.x * kWarps + warp id covers run w % runs of row w / runs, so a
+//     block reads 4 consecutive runs of one row; w / runs = umulhi(w, run_magic) with run_magic = 2^32 / runs + 1
+//     (exact for w * runs < 2^32, checked by the host), or
+//   row map (run_magic == 0): grid.x = runs * ceil(H / kWarps), a block covers the same run of 4 consecutive rows
+//     (blockIdx.x = run + runs * row group would need a division again, so the row map keeps runs in `runs_per_row`
+//     and decodes with the same multiply).
 // The first version decoded a linear 64-bit index with three long-long div/mod pairs: ~150 of the ~580 instructions a
 // warp executed for an image warp (ncu source page, round 2).
-__device__ __forceinline__ RunCoord locate_run(int H, int nchunk, int run_px, int runs_per_row) {
+__device__ __forceinline__ RunCoord locate_run(int H, int run_px, int runs_per_row, unsigned run_magic, int row_map) {
   RunCoord rc;
   const unsigned warp = threadIdx.x >> 5;
   unsigned run;
-  if (runs_per_row > 0) {
+  if (!row_map) {
     const unsigned w = blockIdx.x * kWarps + warp;
-    rc.y = (int)(w / (unsigned)runs_per_row);
+    rc.y = (int)(run_magic ? __umulhi(w, run_magic) : w);                 // run_magic == 0: one run per row
     run = w - (unsigned)rc.y * (unsigned)runs_per_row;
   } else {
-    run = blockIdx.x;
-    rc.y = (int)(blockIdx.y * kWarps + warp);
+    const unsigned yg = run_magic ? __umulhi(blockIdx.x, run_magic) : blockIdx.x;       // row group
+    run = blockIdx.x - yg * (unsigned)runs_per_row;
+    rc.y = (int)(yg * kWarps + warp);
   }
-  rc.b = (int)(blockIdx.z / (unsigned)nchunk);           // block-uniform
-  rc.chunk = (int)blockIdx.z - rc.b * nchunk;
+  rc.chunk = (int)blockIdx.y;
+  rc.b = (int)blockIdx.z;
   rc.x0 = (int)run * run_px;
   rc.live = rc.y < H;
   return rc;
@@ -66,16 +70,18 @@ __device__ __forceinline__ RunCoord locate_run(int H, int nchunk, int run_px, in
 
 // grid for the mapping above; `row_map` selects the second form
 dim3 run_grid(int B, int nchunk, int H, int runs, bool row_map) {
-  return row_map ? dim3(runs, ceil_div(H, kWarps), B * nchunk) : dim3(ceil_div(H * runs, kWarps), 1, B * nchunk);
+  return row_map ? dim3(runs * ceil_div(H, kWarps), nchunk, B) : dim3(ceil_div(H * runs, kWarps), nchunk, B);
 }
+inline unsigned magic_of(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d + 1ull); }
 
 // ---------------------------------------------------------------------------------- NCHW fwd
 template <int PXT, int UNR>
 __global__ void __launch_bounds__(kWarps * 32)
 warp_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out, int B, int C,
-                     int H, int W, int nchunk, int runs_per_row, int use_mask, int align_corners) {
+                     int H, int W, int nchunk, int runs_per_row, unsigned run_magic, int row_map, int use_mask,
+                     int align_corners) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run(H, nchunk, 32 * PXT, runs_per_row);
+  const RunCoord rc = locate_run(H, 32 * PXT, runs_per_row, run_magic, row_map);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const float* fb = flow + (size_t)rc.b * 2 * plane + (size_t)rc.y * W;
@@ -141,9 +147,10 @@ template <int PXT, bool NEED_GX, bool ATOMIC_GFLOW, int UNR>
 __global__ void __launch_bounds__(kWarps * 32)
 warp_bwd_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ x, const float* __restrict__ flow,
                      float* __restrict__ gx, float* __restrict__ gflow, int B, int C, int H, int W, int nchunk,
-                     int runs_per_row, int use_mask, int align_corners, float sx, float sy) {
+                     int runs_per_row, unsigned run_magic, int row_map, int use_mask, int align_corners, float sx,
+                     float sy) {
   const int lane = threadIdx.x & 31;
-  const RunCoord rc = locate_run(H, nchunk, 32 * PXT, runs_per_row);
+  const RunCoord rc = locate_run(H, 32 * PXT, runs_per_row, run_magic, row_map);
   if (!rc.live) return;
   const size_t plane = (size_t)H * W;
   const size_t row = (size_t)rc.y * W;
@@ -395,12 +402,12 @@ extern "C" int uof_warp_fwd(const float* x, const float* flow, float* out, int B
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, false), runs = ceil_div(W, 32 * pxt);
-    UOF_REQUIRE((long long)B * nchunk <= 65535 && ceil_div(H, kWarps) <= 65535, "warp_fwd: grid too large (B*chunks=%lld)", (long long)B * nchunk);
+    UOF_REQUIRE(B <= 65535 && nchunk <= 65535 && (long long)H * runs * runs < (1ll << 31), "warp_fwd: grid too large (B=%d)", B);
     // measured (profiles/r2_warp_map.txt): the forward kernel is faster when a block reads 4 consecutive runs of one row
     static const int fmap = env_int("UOF_WARP_FWD_ROWMAP");
     const dim3 blocks = run_grid(B, nchunk, H, runs, fmap == 1);
-    const int rpr = fmap == 1 ? 0 : runs;
-#define UOF_FWD(P, U) warp_fwd_nchw_kernel<P, U><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, rpr, use_mask, align_corners)
+    const int rmap = fmap == 1 ? 1 : 0;
+#define UOF_FWD(P, U) warp_fwd_nchw_kernel<P, U><<<blocks, kWarps * 32, 0, stream>>>(x, flow, out, B, C, H, W, nchunk, runs, magic_of(runs), rmap, use_mask, align_corners)
     // channels per load batch: 4 for feature maps (measured 30.4 -> 26.4 us at 16x32x64x208), 2 for 3-channel images
     static const int unr_env = env_int("UOF_WARP_UNROLL");
     const int unr = (unr_env == 2 || unr_env == 4) ? unr_env : (C >= 8 ? 4 : 2);
@@ -422,18 +429,18 @@ static void launch_bwd_nchw(const float* gout, const float* x, const float* flow
                             cudaStream_t stream) {
   static const int bmap = env_int("UOF_WARP_BWD_LINMAP");
   const dim3 blocks = run_grid(B, nchunk, H, runs, bmap != 1);
-  const int rpr = bmap != 1 ? 0 : runs;
+  const int rmap = bmap != 1 ? 1 : 0;
+  const unsigned magic = magic_of(runs);
   static const int unr_env = env_int("UOF_WARP_UNROLL");
   const int unr = (unr_env == 2 || unr_env == 4) ? unr_env : (C >= 8 ? 4 : 2);
 #define UOF_LAUNCH(GX, AT)                                                                                              \
   do {                                                                                                                  \
     if (unr == 4 && PXT == 1)                                                                                           \
       warp_bwd_nchw_kernel<PXT, GX, AT, (PXT == 1 ? 4 : 2)><<<blocks, kWarps * 32, 0, stream>>>(                         \
-          gout, x, flow, gx, gflow, B, C, H, W, nchunk, rpr, use_mask, align_corners, sx, sy);                          \
+          gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, magic, rmap, use_mask, align_corners, sx, sy);            \
     else                                                                                                                \
-      warp_bwd_nchw_kernel<PXT, GX, AT, 2><<<blocks, kWarps * 32, 0, stream>>>(gout, x, flow, gx, gflow, B, C, H, W,    \
-                                                                               nchunk, rpr, use_mask, align_corners,   \
-                                                                               sx, sy);                                 \
+      warp_bwd_nchw_kernel<PXT, GX, AT, 2><<<blocks, kWarps * 32, 0, stream>>>(                                         \
+          gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, magic, rmap, use_mask, align_corners, sx, sy);            \
   } while (0)
   if (gx) {
     if (nchunk > 1) UOF_LAUNCH(true, true); else UOF_LAUNCH(true, false);
@@ -452,7 +459,7 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
   if (gx) UOF_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * C * H * W * sizeof(float), stream));
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, true), runs = ceil_div(W, 32 * pxt);
-    UOF_REQUIRE((long long)B * nchunk <= 65535 && ceil_div(H, kWarps) <= 65535, "warp_bwd: grid too large (B*chunks=%lld)", (long long)B * nchunk);
+    UOF_REQUIRE(B <= 65535 && nchunk <= 65535 && (long long)H * runs * runs < (1ll << 31), "warp_bwd: grid too large (B=%d)", B);
     if (nchunk > 1) UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
     if (pxt == 4)
       launch_bwd_nchw<4>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);

@@ -113,7 +113,7 @@ def cases(B=8, H=256, W=832):
         for s in range(S):
             lv[s] = PhotoLevel(imgs[s].data_ptr(), both[s][:B].data_ptr(), both[s][B:].data_ptr(), wl[s].data_ptr(),
                                wr[s].data_ptr(), None, None, gb[s][:B].data_ptr(), gb[s][B:].data_ptr(), H >> s, W >> s)
-        sums, lp, ls = torch.zeros(S, B, 6, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev)
+        sums, lp, ls = torch.zeros(S * B * 6 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev)
         g = torch.ones(B, device=dev)
         keep.append((imgs, both, wl, wr, gb, lv, sums, lp, ls, g))
         return imgs, wr, lv, sums, lp, ls, g
@@ -133,8 +133,8 @@ def cases(B=8, H=256, W=832):
         for s in range(S):
             sl[s] = SmoothLevel(fl[s].data_ptr(), imgs[s].data_ptr(), gf[s].data_ptr(), H >> s, W >> s)
             cl[s] = ConsisLevel(fl[s][B:].data_ptr(), fl[s][:B].data_ptr(), wr[s].data_ptr(), gf[s][B:].data_ptr(), H >> s, W >> s)
-        ssum, sloss = torch.zeros(S, B2, 2, device=dev), torch.empty(B2, device=dev)
-        csum, closs = torch.zeros(S, B, 2, device=dev), torch.empty(B, device=dev)
+        ssum, sloss = torch.zeros(S * B2 * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B2, device=dev)
+        csum, closs = torch.zeros(S * B * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev)
         g2 = torch.ones(B2, device=dev)
         keep.append((fl, gf, sl, cl, ssum, sloss, csum, closs, g2))
         return sl, cl, ssum, sloss, csum, closs, g2

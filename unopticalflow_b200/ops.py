@@ -223,7 +223,7 @@ class _PhotoLoss(torch.autograd.Function):
                                weights_l[s].data_ptr(), weights_r[s].data_ptr(),
                                diffs_l[s].data_ptr() if want_diff else None, diffs_r[s].data_ptr() if want_diff else None,
                                None, None, H, W)
-        sums = torch.empty((S, B, 6), device=dev)
+        sums = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, device=dev)      # (S,B,6) partial sums + the kernel's block counter
         loss_pixel, loss_ssim = torch.empty(B, device=dev), torch.empty(B, device=dev)
         with torch.cuda.device_of(imgs[0]):
             _lib.call('uof_photo_loss_fwd', lv, S, B, _p(sums), _p(loss_pixel), _p(loss_ssim), _stream(imgs[0]))
@@ -258,8 +258,8 @@ class _PhotoLoss(torch.autograd.Function):
             _, _, H, W = imgs[s].shape
             lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), wmaps[s].data_ptr(),
                                wmaps[S + s].data_ptr(), None, None, gl[s].data_ptr(), gr[s].data_ptr(), H, W)
-        g_pixel = torch.zeros_like(sums[0, :, 0]) if g_pixel is None else g_pixel.contiguous()
-        g_ssim = torch.zeros_like(sums[0, :, 0]) if g_ssim is None else g_ssim.contiguous()
+        g_pixel = torch.zeros(B, device=sums.device) if g_pixel is None else g_pixel.contiguous()
+        g_ssim = torch.zeros(B, device=sums.device) if g_ssim is None else g_ssim.contiguous()
         with torch.cuda.device_of(sums):
             _lib.call('uof_photo_loss_bwd', lv, S, B, _p(sums), _p(g_pixel), _p(g_ssim), _stream(sums))
         if stacked:
@@ -387,7 +387,7 @@ class _SmoothLoss(torch.autograd.Function):
             _, _, H, W = flows[s].shape
             assert imgs[s].shape[2:] == flows[s].shape[2:]
             lv[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), None, H, W)
-        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev)
         with torch.cuda.device_of(flows[0]):
             _lib.call('uof_smooth_loss_fwd', lv, S, B, Bimg, _p(sums), _p(loss), _stream(flows[0]))
         ctx.save_for_backward(*flows, *imgs)
@@ -431,7 +431,7 @@ class _ConsisLoss(torch.autograd.Function):
         for s in range(S):
             _, _, H, W = ff[s].shape
             lv[s] = ConsisLevel(ff[s].data_ptr(), fb[s].data_ptr(), wf[s].data_ptr(), None, H, W)
-        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev)
         with torch.cuda.device_of(ff[0]):
             _lib.call('uof_consis_loss_fwd', lv, S, B, _p(sums), _p(loss), _stream(ff[0]))
         ctx.save_for_backward(sums, *ff, *fb, *wf)
