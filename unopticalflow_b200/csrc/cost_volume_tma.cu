@@ -20,7 +20,8 @@ namespace uof {
 namespace cv {
 namespace {
 
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 3;      // backward: 3 slabs + two reduction buffers = 110 KB per CTA, 2 CTAs per SM
+constexpr int NSTAGE_F = 3;    // forward; a 4th stage (106-112 KB per CTA, still 2 CTAs per SM) measured no gain (41.4 vs 41.3 us)
 constexpr int NWARP = NT / 32;
 
 template <int TH_, int TW_>
@@ -58,8 +59,8 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
   constexpr int kStage = S1 + S2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* smem = align128(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * kStage);
-  uint64_t* empty = full + NSTAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE_F * kStage);
+  uint64_t* empty = full + NSTAGE_F;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int gx = tid % T::QX, ty = T::row_of((tid / T::QX) % TH), dg = tid / T::QUADS;
@@ -73,7 +74,7 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NSTAGE_F; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, NWARP);
     }
@@ -84,14 +85,14 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
   __syncthreads();
 
   auto issue = [&](int j) {
-    const int s = j % NSTAGE;
+    const int s = j % NSTAGE_F;
     float* dst = smem + s * kStage;
     mbar_expect_tx(full + s, kStage * (unsigned)sizeof(float));
     tma_load_4d(dst, &map1, full + s, x0, y0, (k_begin + j) * CK, b);
     tma_load_4d(dst + S1, &map2, full + s, x0 - RAD, y0 - RAD, (k_begin + j) * CK, b);
   };
   if (tid == 0)
-    for (int j = 0; j < min(NSTAGE - 1, n); ++j) issue(j);
+    for (int j = 0; j < min(NSTAGE_F - 1, n); ++j) issue(j);
 
   float acc[DYG][ND][PX];
 #pragma unroll
@@ -103,14 +104,14 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 
   for (int j = 0; j < n; ++j) {
     if (tid == 0) {   // refill the stage consumed one iteration ago
-      const int jj = j + NSTAGE - 1;
+      const int jj = j + NSTAGE_F - 1;
       if (jj < n) {
-        if (j >= 1) mbar_wait(empty + (j - 1) % NSTAGE, ((j - 1) / NSTAGE) & 1);
+        if (j >= 1) mbar_wait(empty + (j - 1) % NSTAGE_F, ((j - 1) / NSTAGE_F) & 1);
         issue(jj);
       }
     }
-    const int s = j % NSTAGE;
-    mbar_wait(full + s, (j / NSTAGE) & 1);
+    const int s = j % NSTAGE_F;
+    mbar_wait(full + s, (j / NSTAGE_F) & 1);
     const float* a_base = smem + s * kStage + ty * TW + PX * gx;
     const float* w_base = smem + s * kStage + S1 + (ty + dg * DYG) * HTW + PX * gx;
 #pragma unroll 2
@@ -148,6 +149,121 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 #pragma unroll
         for (int p = 0; p < PX; ++p) atomicAdd(o + p, acc[r][jd][p] * inv_c);
       }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- forward, persistent
+// Same math and tiling, but a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (grid = 2 CTAs per SM) and the
+// slab pipeline runs across tile boundaries: the producer keeps issuing the next tile's TMA loads while the consumers
+// finish the current tile and write it out, so the per-tile pipeline fill (barrier init, descriptor prefetch, first TMA
+// round trip -- ~10-20 % of a 4-slab tile at C = 32, during which the SM's other CTA computes alone with 1.5 warps per
+// scheduler) is paid once per CTA instead of once per tile.  Used when the level has more tiles than resident CTAs and
+// no split-K.
+template <class T>
+__global__ void __launch_bounds__(NT, 2)
+cost_volume_fwd_tma_persistent_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                                      float* __restrict__ out, int C, int H, int W, long long out_bs, float inv_c,
+                                      int tiles_x, int tiles_y, int total_tiles) {
+  constexpr int TH = T::TH, TW = T::TW, HTH = T::HTH, HTW = T::HTW, S1 = T::S1, S2 = T::S2;
+  constexpr int kStage = S1 + S2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* smem = align128(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE_F * kStage);
+  uint64_t* empty = full + NSTAGE_F;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gx = tid % T::QX, ty = T::row_of((tid / T::QX) % TH), dg = tid / T::QUADS;
+  const int n = (C + CK - 1) / CK;                                   // slabs per tile
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * n;                                    // slabs this CTA consumes
+  if (total <= 0) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE_F; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NWARP);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&map1);
+    tma_prefetch_desc(&map2);
+  }
+  __syncthreads();
+
+  // tile index -> origin; tiles of one image are consecutive (x fastest) so neighbouring CTAs share halos in L2
+  auto origin = [&](int t, int& x0, int& y0, int& b) {
+    const int bx = t % tiles_x;
+    const int r = t / tiles_x;
+    x0 = bx * TW;
+    y0 = (r % tiles_y) * TH;
+    b = r / tiles_y;
+  };
+  auto issue = [&](int q) {                                            // q-th slab of this CTA's sequence
+    int x0, y0, b;
+    origin((int)blockIdx.x + (q / n) * (int)gridDim.x, x0, y0, b);
+    const int j = q % n, s = q % NSTAGE_F;
+    float* dst = smem + s * kStage;
+    mbar_expect_tx(full + s, kStage * (unsigned)sizeof(float));
+    tma_load_4d(dst, &map1, full + s, x0, y0, j * CK, b);
+    tma_load_4d(dst + S1, &map2, full + s, x0 - RAD, y0 - RAD, j * CK, b);
+  };
+  if (tid == 0)
+    for (int q = 0; q < min(NSTAGE_F - 1, total); ++q) issue(q);
+
+  float acc[DYG][ND][PX];
+  int q = 0;
+  for (int it = 0; it < my_tiles; ++it) {
+#pragma unroll
+    for (int r = 0; r < DYG; ++r)
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+#pragma unroll
+        for (int p = 0; p < PX; ++p) acc[r][j][p] = 0.0f;
+
+    for (int j = 0; j < n; ++j, ++q) {
+      if (tid == 0) {   // refill the stage consumed one iteration ago (possibly with a slab of the NEXT tile)
+        const int qq = q + NSTAGE_F - 1;
+        if (qq < total) {
+          if (q >= 1) mbar_wait(empty + (q - 1) % NSTAGE_F, ((q - 1) / NSTAGE_F) & 1);
+          issue(qq);
+        }
+      }
+      const int s = q % NSTAGE_F;
+      mbar_wait(full + s, (q / NSTAGE_F) & 1);
+      const float* a_base = smem + s * kStage + ty * TW + PX * gx;
+      const float* w_base = smem + s * kStage + S1 + (ty + dg * DYG) * HTW + PX * gx;
+#pragma unroll 2
+      for (int cc = 0; cc < CK; ++cc) {
+        const float4 a4 = *reinterpret_cast<const float4*>(a_base + cc * TH * TW);
+        const float a[PX] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int r = 0; r < DYG; ++r) {
+          const float4* wp = reinterpret_cast<const float4*>(w_base + cc * HTH * HTW + r * HTW);
+          const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+          const float win[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+          for (int jd = 0; jd < ND; ++jd)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[r][jd][p] = fmaf(a[p], win[p + jd], acc[r][jd][p]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+
+    int x0, y0, b;
+    origin((int)blockIdx.x + it * (int)gridDim.x, x0, y0, b);
+    const int y = y0 + ty, x = x0 + PX * gx;
+    if (y < H && x < W) {
+      float* ob = out + (size_t)b * out_bs + (size_t)y * W + x;
+      const size_t plane = (size_t)H * W;
+#pragma unroll
+      for (int r = 0; r < DYG; ++r)
+#pragma unroll
+        for (int jd = 0; jd < ND; ++jd)
+          *reinterpret_cast<float4*>(ob + (size_t)((dg * DYG + r) * ND + jd) * plane) =
+              make_float4(acc[r][jd][0] * inv_c, acc[r][jd][1] * inv_c, acc[r][jd][2] * inv_c, acc[r][jd][3] * inv_c);
     }
   }
 }
@@ -279,7 +395,7 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 
 template <class T>
 constexpr size_t fwd_smem() {
-  return NSTAGE * (T::S1 + T::S2) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 128;
+  return NSTAGE_F * (T::S1 + T::S2) * sizeof(float) + 2 * NSTAGE_F * sizeof(uint64_t) + 128;
 }
 template <class T>
 constexpr size_t bwd_smem() {
@@ -327,6 +443,15 @@ int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H
   UOF_REQUIRE((long long)B * ksplit <= 65535 && ty <= 65535, "cost_volume_fwd: grid too large");
   if (ksplit > 1)
     UOF_CUDA(cudaMemset2DAsync(out, out_bs * sizeof(float), 0, (size_t)UOF_NUM_DISPLACEMENTS * H * W * sizeof(float), B, stream));
+  const long long tiles = (long long)tx * ty * B;
+  static const bool no_persist = getenv("UOF_CV_NO_PERSIST") != nullptr;
+  if (ksplit == 1 && tiles > 2 * kNumSMs && tiles < (1ll << 30) && !no_persist) {
+    auto pk = cost_volume_fwd_tma_persistent_kernel<T>;
+    UOF_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<T>()));
+    pk<<<2 * kNumSMs, NT, fwd_smem<T>(), stream>>>(m1, m2, out, C, H, W, out_bs, 1.0f / (float)C, tx, ty, (int)tiles);
+    count_launch();
+    return check_launch("cost_volume_fwd (tma, persistent)");
+  }
   auto kern = cost_volume_fwd_tma_kernel<T>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<T>()));
   kern<<<dim3(tx, ty, B * ksplit), NT, fwd_smem<T>(), stream>>>(m1, m2, out, C, H, W, out_bs, ksplit, 1.0f / (float)C);
