@@ -380,6 +380,50 @@ def test_smooth_and_consis_vs_oracle(U, B, H, W):
     assert_close(s2[B:], sf, 1e-6)
 
 
+def test_loss_kernels_full_size_vs_same_gpu_oracle(U):
+    """BASELINE config 2 shapes (B=8, 256x832, three scales, flows stacked [bwd;fwd] as Model_flow.forward does): every
+    fused loss kernel -- multi-strip, multi-level, quad / pair layouts -- against the oracle's op chain executed on the same
+    GPU (the CPU oracle needs minutes at this size).  Values and gradients within 1e-4 relative."""
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(2024)
+    B, H, W, S = 8, 256, 832, 3
+    r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+    imgs = [O.img_pyramid(r(B, 3, H, W), S) for _ in range(3)]
+    lo = (r(2 * B, 2, H // 8, W // 8) - 0.5) * 6.0
+    flows = [torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)
+             + (r(2 * B, 2, H >> s, W >> s) - 0.5) * 0.5 for s in range(S)]
+    with torch.no_grad():
+        from_l = [O.warp_flow(imgs[0][s], flows[s][:B], use_mask=True) for s in range(S)]
+        from_r = [O.warp_flow(imgs[2][s], flows[s][B:], use_mask=True) for s in range(S)]
+    ct = torch.randn(4, 2 * B, device=dev, generator=g)
+
+    def losses(use_cuda_kernels):
+        fl = [f.clone().requires_grad_(True) for f in flows]
+        wl = [t.clone().requires_grad_(True) for t in from_l]
+        wr = [t.clone().requires_grad_(True) for t in from_r]
+        if use_cuda_kernels:
+            pix, ssim, w_b, w_f = U.ops.photometric_losses(imgs[1], wl, wr, S)
+            smooth = U.ops.flow_smooth_loss(fl, imgs[1], S)
+            consis = U.ops.flow_consis_loss([f[B:] for f in fl], [f[:B] for f in fl], w_f, S)
+        else:
+            d_b, d_f, w_b, w_f = O.diff_weight(wl, imgs[1], wr, S)
+            pix = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+            ssim = O.loss_ssim(imgs[1], wr, w_f, S) + O.loss_ssim(imgs[1], wl, w_b, S)
+            smooth = torch.cat((O.loss_flow_smooth([f[:B] for f in fl], imgs[1], S), O.loss_flow_smooth([f[B:] for f in fl], imgs[1], S)))
+            consis = O.loss_flow_consis([f[B:] for f in fl], [f[:B] for f in fl], w_f, S)
+        total = (pix * ct[0, :B]).sum() + (ssim * ct[1, :B]).sum() + (smooth * ct[2]).sum() * 100.0 + (consis * ct[3, :B]).sum()
+        grads = torch.autograd.grad(total, fl + wl + wr)
+        return (pix, ssim, smooth, consis), grads
+
+    (vals, grads), (rvals, rgrads) = losses(True), losses(False)
+    for name, a, b in zip(('loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis'), vals, rvals):
+        assert a.shape == b.shape
+        assert_close(a, b, REL_TOL, name + ' at 8x256x832')
+    for i, (a, b) in enumerate(zip(grads, rgrads)):
+        assert float(b.abs().max()) > 0
+        assert_close(a, b, REL_TOL, 'gradient %d at 8x256x832' % i)
+
+
 def test_losses_golden_from_reference(U):
     """Inputs and outputs recorded from the unmodified reference (tests/golden/losses.npz): warp with mask,
     weights, all four losses and their flow gradients through the CUDA path."""
