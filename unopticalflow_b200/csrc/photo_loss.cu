@@ -187,6 +187,152 @@ photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__
   block_accumulate<6, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 6 : nullptr);
 }
 
+// horizontal 3-tap moments of a pixel pair: left neighbour of px0 / right neighbour of px1 come from the adjacent lanes
+__device__ __forceinline__ void pair_moments(float x0, float y0, float x1, float y1, float* m0, float* m1) {
+  const float xl = __shfl_up_sync(kFullMask, x1, 1), yl = __shfl_up_sync(kFullMask, y1, 1);      // left neighbour of px0
+  const float xr = __shfl_down_sync(kFullMask, x0, 1), yr = __shfl_down_sync(kFullMask, y0, 1);  // right neighbour of px1
+  const float sx = x0 + x1, sy = y0 + y1;
+  const float sxx = fmaf(x1, x1, x0 * x0), syy = fmaf(y1, y1, y0 * y0), sxy = fmaf(x1, y1, x0 * y0);
+  m0[0] = sx + xl;            m1[0] = sx + xr;
+  m0[1] = sy + yl;            m1[1] = sy + yr;
+  m0[2] = fmaf(xl, xl, sxx);  m1[2] = fmaf(xr, xr, sxx);
+  m0[3] = fmaf(yl, yl, syy);  m1[3] = fmaf(yr, yr, syy);
+  m0[4] = fmaf(xl, yl, sxy);  m1[4] = fmaf(xr, yr, sxy);
+}
+
+
+// ------------------------------------------------------- forward, direction-split pixel-pair variant (default)
+// The fused-direction kernel above is instruction-issue bound (ncu, round 2: ~490 instructions per warp-row of 30 pixels,
+// issue slots 74 % busy, FMA pipe 45 %, DRAM 21 %).  This variant halves the issued instructions per pixel:
+//   * a warp owns ONE direction and TWO adjacent columns per lane (64 columns per strip, 60 of them outputs), so the
+//     addressing / predicate / shuffle overhead is amortised over two pixels and the 3x5 moment state of one direction
+//     (last + pair: 60 registers for the pixel pair) fits without spills;
+//   * everything that is the same arithmetic on both pixels -- the vertical window sums and the whole SSIM formula -- runs
+//     as packed fp32 (fma.rn.f32x2 / add.f32x2 / mul.f32x2, Blackwell's FFMA2 / FADD2 / FMUL2): one issue slot for two
+//     pixels.  FFMA2 has the same FLOP throughput as FFMA (profiles/microbench), which is why it did not help the
+//     FMA-bound cost volume, but it halves the issue pressure of an issue-bound kernel;
+//   * rows arrive through a per-warp cp.async ring (9 float2 planes, zero-filled outside the image -- a zero pixel has
+//     valid = 0, hence weight 0, so no further masking is needed).
+// The two direction warps of a strip sit in the same block (shared L1 lines); both evaluate the weight pair, which needs
+// all nine values of a pixel.  Requires even W and 8-byte aligned planes at every level.
+constexpr int kFwdPairDepth = 3;
+typedef float2 f2;
+__device__ __forceinline__ f2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+
+// SSIM of two pixels at once from their raw window sums (see ssim_from_total)
+__device__ __forceinline__ f2 ssim2(f2 Sx, f2 Sy, f2 Sxx, f2 Syy, f2 Sxy) {
+  const f2 m1 = splat2(-1.0f), nine = splat2(9.0f);
+  const f2 pxy = mul2(Sx, Sy), pxx = mul2(Sx, Sx), pyy = mul2(Sy, Sy);
+  const f2 A1 = fma2(splat2(2.0f), pxy, splat2(C1x81));
+  const f2 A2 = fma2(splat2(2.0f), fma2(nine, Sxy, mul2(pxy, m1)), splat2(C2x81));
+  const f2 B1 = add2(add2(pxx, pyy), splat2(C1x81));
+  const f2 B2 = add2(add2(fma2(nine, Sxx, mul2(pxx, m1)), fma2(nine, Syy, mul2(pyy, m1))), splat2(C2x81));
+  const f2 D = mul2(B1, B2);
+  const f2 invD = make_float2(__fdividef(1.0f, D.x), __fdividef(1.0f, D.y));
+  return mul2(mul2(A1, A2), invD);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+photo_loss_fwd_pair_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
+  __shared__ float2 ring_s[kWarpsPerBlock][kFwdPairDepth * 9 * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int dir = wid & 1;                                   // 0: left / "bwd", 1: right / "fwd"
+  Strip sc;
+  const bool live = locate_strip<2, 2>(P.T, blockIdx.x * (kWarpsPerBlock / 2) + (wid >> 1), lane, sc);
+  if (!live) sc.level = sc.b = sc.col = sc.y0 = sc.y1 = 0;   // idle warps still join the block reduction at the end
+  const uof_photo_level& L = P.lv[sc.level];
+  const int H = L.H, W = L.W;
+  const unsigned plane = (unsigned)(H * W);
+  const bool pin = sc.col >= 0 && sc.col < W;                // W even: the pair is entirely inside or outside
+  const bool pout = pin && lane >= 1 && lane <= 30;
+  const unsigned colc = (unsigned)min(max(sc.col, 0), W - 2);
+  const unsigned img_base = (unsigned)sc.b * 3u * plane + colc, map_base = (unsigned)sc.b * plane + colc;
+  const float* __restrict__ img = L.img + img_base;
+  const float* __restrict__ wpl = L.warped_l + img_base;
+  const float* __restrict__ wpr = L.warped_r + img_base;
+  float* __restrict__ wmap = dir ? L.weight_r : L.weight_l;
+  float* __restrict__ dmap = dir ? L.diff_r : L.diff_l;
+
+  f2 last[3][5], pair[3][5];                                 // [channel][moment], the two pixels packed
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) last[c][k] = pair[c][k] = splat2(0.0f);
+  float acc_l1 = 0.0f, acc_w = 0.0f;
+  f2 acc_ss = splat2(0.0f);
+
+  if (live) {
+    float2* ring = ring_s[wid] + lane;
+    auto fetch = [&](int r, int slot) {
+      const bool inb = pin && r >= 0 && r < H;
+      const unsigned o = (unsigned)min(max(r, 0), H - 1) * W;
+      float2* d = ring + slot * (9 * 32);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        cp_async_8(d + c * 32, img + c * plane + o, inb);
+        cp_async_8(d + (3 + c) * 32, wpl + c * plane + o, inb);
+        cp_async_8(d + (6 + c) * 32, wpr + c * plane + o, inb);
+      }
+      cp_async_commit();
+    };
+    const int r_begin = sc.y0 - 1, r_end = sc.y1;
+#pragma unroll
+    for (int i = 0; i < kFwdPairDepth - 1; ++i) fetch(r_begin + i, i);
+    int slot = 0;
+    for (int r = r_begin; r <= r_end; ++r) {
+      fetch(r + kFwdPairDepth - 1, slot == 0 ? kFwdPairDepth - 1 : slot - 1);
+      cp_async_wait<kFwdPairDepth - 1>();
+      f2 v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = ring[slot * (9 * 32) + k * 32];
+      slot = slot + 1 == kFwdPairDepth ? 0 : slot + 1;
+
+      // weights of both pixels (model_flow_paper.py:111-129); an all-zero (out-of-image) pixel gets weight 0
+      const float p0[9] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x, v[8].x};
+      const float p1[9] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y, v[8].y};
+      const PixelWeights w0 = pixel_weights(p0), w1 = pixel_weights(p1);
+      const f2 w = dir ? make_float2(w0.wr, w1.wr) : make_float2(w0.wl, w1.wl);
+      if (pout && r >= sc.y0 && r < sc.y1) {
+        const f2 dd = dir ? make_float2(w0.dr, w1.dr) : make_float2(w0.dl, w1.dl);
+        acc_l1 = fmaf(dd.y, w.y, fmaf(dd.x, w.x, acc_l1));
+        acc_w += w.x + w.y;
+        const unsigned off = map_base + (unsigned)r * W;
+        if (wmap) *reinterpret_cast<float2*>(wmap + off) = w;
+        if (dmap) *reinterpret_cast<float2*>(dmap + off) = dd;
+      }
+      const bool emit = r - 1 >= sc.y0 && pout;              // row q = r-1 now has its full 3x3 window
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const f2 x = mul2(v[c], w), y = mul2(v[3 + 3 * dir + c], w);
+        float m0[5], m1[5];
+        pair_moments(x.x, y.x, x.y, y.y, m0, m1);
+        f2 h[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) h[k] = make_float2(m0[k], m1[k]);
+        if (emit) {
+          const f2 S = ssim2(add2(pair[c][0], h[0]), add2(pair[c][1], h[1]), add2(pair[c][2], h[2]), add2(pair[c][3], h[3]),
+                             add2(pair[c][4], h[4]));
+          const f2 t = fma2(splat2(-0.5f), S, splat2(0.5f));   // clamp((1-S)/2, 0, 1), model_flow_paper.py:144
+          acc_ss = add2(acc_ss, make_float2(__saturatef(t.x), __saturatef(t.y)));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          pair[c][k] = add2(last[c][k], h[k]);
+          last[c][k] = h[k];
+        }
+      }
+    }
+    cp_async_wait<0>();
+  }
+  // sums layout: [0]=sum d_l*w_l [1]=sum w_l [2]=sum d_r*w_r [3]=sum w_r [4]=ssim_l [5]=ssim_r
+  const float l1 = warp_sum(acc_l1), ws = warp_sum(acc_w), ss = warp_sum(acc_ss.x + acc_ss.y);
+  const float acc[6] = {dir ? 0.0f : l1, dir ? 0.0f : ws, dir ? l1 : 0.0f, dir ? ws : 0.0f, dir ? 0.0f : ss, dir ? ss : 0.0f};
+  block_accumulate<6, kWarpsPerBlock>(acc, live ? sums + ((size_t)sc.level * P.T.B + sc.b) * 6 : nullptr);
+}
+
 // loss_pixel[b] = sum_l sum_d mean(d*w)/(mean(w)+eps);  loss_ssim[b] likewise (model_flow_paper.py:94-98,141-147).
 // A separate one-block launch: folding it into the forward kernel ("last block" pattern, as smooth_fwd does) was measured
 // SLOWER here (59.7 -> 69.6 us): the per-block __threadfence has to drain the block's weight-map stores and the counter
@@ -444,18 +590,6 @@ photo_loss_bwd_split_kernel(const __grid_constant__ PhotoParams P, const float* 
 // warp-row, ~75 of them addressing/predication/control: the pair layout amortises that overhead over two pixels,
 // halves the shuffles per pixel (2 instead of 4 per quantity and pair) and shrinks the column halo from 4/32 to 4/64.
 // Requires even W at every level (pairs are then entirely inside or outside the image).
-__device__ __forceinline__ void pair_moments(float x0, float y0, float x1, float y1, float* m0, float* m1) {
-  const float xl = __shfl_up_sync(kFullMask, x1, 1), yl = __shfl_up_sync(kFullMask, y1, 1);      // left neighbour of px0
-  const float xr = __shfl_down_sync(kFullMask, x0, 1), yr = __shfl_down_sync(kFullMask, y0, 1);  // right neighbour of px1
-  const float sx = x0 + x1, sy = y0 + y1;
-  const float sxx = fmaf(x1, x1, x0 * x0), syy = fmaf(y1, y1, y0 * y0), sxy = fmaf(x1, y1, x0 * y0);
-  m0[0] = sx + xl;            m1[0] = sx + xr;
-  m0[1] = sy + yl;            m1[1] = sy + yr;
-  m0[2] = fmaf(xl, xl, sxx);  m1[2] = fmaf(xr, xr, sxx);
-  m0[3] = fmaf(yl, yl, syy);  m1[3] = fmaf(yr, yr, syy);
-  m0[4] = fmaf(xl, yl, sxy);  m1[4] = fmaf(xr, yr, sxy);
-}
-
 __device__ __forceinline__ void ssim_coeffs(const float* s0, const float* s1, const float* s2, bool live, float coef_ss,
                                             float* abc) {
   abc[0] = abc[1] = abc[2] = 0.0f;
@@ -468,6 +602,33 @@ __device__ __forceinline__ void ssim_coeffs(const float* s0, const float* s1, co
     abc[1] = -9.0f * k * t.S * t.B1;
     abc[2] = 18.0f * k * t.A1;
   }
+}
+
+// ssim_coeffs for the two pixels of a pair at once, in packed fp32 (FFMA2 / FADD2 / FMUL2: one issue slot per pixel pair)
+__device__ __forceinline__ void ssim_coeffs2(const f2* s0, const f2* s1, const f2* s2, bool live, float coef_ss, f2* abc) {
+  const f2 m1 = splat2(-1.0f), nine = splat2(9.0f);
+  const f2 Sx = add2(add2(s0[0], s1[0]), s2[0]), Sy = add2(add2(s0[1], s1[1]), s2[1]);
+  const f2 Sxx = add2(add2(s0[2], s1[2]), s2[2]), Syy = add2(add2(s0[3], s1[3]), s2[3]), Sxy = add2(add2(s0[4], s1[4]), s2[4]);
+  const f2 pxy = mul2(Sx, Sy), pxx = mul2(Sx, Sx), pyy = mul2(Sy, Sy);
+  const f2 A1 = fma2(splat2(2.0f), pxy, splat2(C1x81));
+  const f2 A2 = fma2(splat2(2.0f), fma2(nine, Sxy, mul2(pxy, m1)), splat2(C2x81));
+  const f2 B1 = add2(add2(pxx, pyy), splat2(C1x81));
+  const f2 B2 = add2(add2(fma2(nine, Sxx, mul2(pxx, m1)), fma2(nine, Syy, mul2(pyy, m1))), splat2(C2x81));
+  const f2 D = mul2(B1, B2);
+  const f2 invD = make_float2(__fdividef(1.0f, D.x), __fdividef(1.0f, D.y));
+  const f2 S = mul2(mul2(A1, A2), invD);
+  const f2 term = fma2(splat2(-0.5f), S, splat2(0.5f));
+  const f2 k = mul2(splat2(coef_ss), invD);
+  const f2 dN = mul2(add2(Sx, Sx), fma2(A1, m1, A2));            // 2 Sx (A2 - A1)
+  const f2 dD = mul2(add2(Sy, Sy), fma2(B1, m1, B2));            // 2 Sy (B2 - B1)
+  const f2 a = mul2(k, fma2(mul2(S, m1), dD, dN));               // dS/dSy  = (dN - S dD) / D
+  const f2 b = mul2(mul2(splat2(-9.0f), k), mul2(S, B1));        // dS/dSyy = -9 S B1 / D
+  const f2 c = mul2(mul2(splat2(18.0f), k), A1);                 // dS/dSxy = 18 A1 / D
+  const bool on0 = live && term.x >= 0.0f && term.x <= 1.0f;     // clamp passes gradient on the closed interval
+  const bool on1 = live && term.y >= 0.0f && term.y <= 1.0f;
+  abc[0] = make_float2(on0 ? a.x : 0.0f, on1 ? a.y : 0.0f);
+  abc[1] = make_float2(on0 ? b.x : 0.0f, on1 ? b.y : 0.0f);
+  abc[2] = make_float2(on0 ? c.x : 0.0f, on1 ? c.y : 0.0f);
 }
 
 __global__ void __launch_bounds__(kSplitWarps * 32)
@@ -496,17 +657,17 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
   const float coef_l1 = __ldg(g_pixel + sc.b) * inv_div / n / 3.0f;
   const float coef_ss = -0.5f * __ldg(g_ssim + sc.b) * inv_div / (3.0f * n);
 
-  float mom[3][2][5], abc[3][2][3], xy[3][2][2], wl1[3][2][2];
+  // state of the pixel pair, packed (.x = first column, .y = second): the vertical sums, the SSIM derivative and the
+  // final blend are identical arithmetic on both pixels and run as packed fp32, one issue slot for the pair
+  f2 mom[3][5], abc[3][3], xy[3][2], wl1[3][2];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 3; ++a) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int j = 0; j < 5; ++j) mom[a][j] = splat2(0.0f);
 #pragma unroll
-      for (int j = 0; j < 5; ++j) mom[a][k][j] = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) abc[a][k][j] = 0.0f;
-      xy[a][k][0] = xy[a][k][1] = wl1[a][k][0] = wl1[a][k][1] = 0.0f;
-    }
+    for (int j = 0; j < 3; ++j) abc[a][j] = splat2(0.0f);
+    xy[a][0] = xy[a][1] = wl1[a][0] = wl1[a][1] = splat2(0.0f);
+  }
 
   const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
   // Row pipeline: a per-warp shared-memory ring of kPairDepth rows x (I, W, w) float2 pairs, kPairDepth-1 rows kept in
@@ -538,44 +699,40 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
       const float2 vI = ring[slot * 96], vW = ring[slot * 96 + 32], vw = ring[slot * 96 + 64];
       slot = slot + 1 == kPairDepth ? 0 : slot + 1;
       const float d0 = vI.x - vW.x, d1 = vI.y - vW.y;
-      wl1[u][0][0] = vw.x;
-      wl1[u][1][0] = vw.y;
-      wl1[u][0][1] = (d0 > 0.0f ? -coef_l1 : (d0 < 0.0f ? coef_l1 : 0.0f)) * vw.x;   // d(masked L1)/dW = -sign(I-W) w coef
-      wl1[u][1][1] = (d1 > 0.0f ? -coef_l1 : (d1 < 0.0f ? coef_l1 : 0.0f)) * vw.y;
-      xy[u][0][0] = vI.x * vw.x; xy[u][0][1] = vW.x * vw.x;
-      xy[u][1][0] = vI.y * vw.y; xy[u][1][1] = vW.y * vw.y;
-      pair_moments(xy[u][0][0], xy[u][0][1], xy[u][1][0], xy[u][1][1], mom[u][0], mom[u][1]);
+      wl1[u][0] = vw;
+      // d(masked L1)/dW = -sign(I-W) w coef
+      wl1[u][1] = mul2(make_float2(d0 > 0.0f ? -coef_l1 : (d0 < 0.0f ? coef_l1 : 0.0f), d1 > 0.0f ? -coef_l1 : (d1 < 0.0f ? coef_l1 : 0.0f)), vw);
+      xy[u][0] = mul2(vI, vw);
+      xy[u][1] = mul2(vW, vw);
+      {
+        float m0[5], m1[5];
+        pair_moments(xy[u][0].x, xy[u][1].x, xy[u][0].y, xy[u][1].y, m0, m1);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) mom[u][j] = make_float2(m0[j], m1[j]);
+      }
 
       const int q = r - 1;
       if (q >= sc.y0 - 1) {
         const bool q_in = pin && q >= 0 && q < H;
-        float c0[3], c1[3];
-        ssim_coeffs(mom[0][0], mom[1][0], mom[2][0], q_in, coef_ss, c0);
-        ssim_coeffs(mom[0][1], mom[1][1], mom[2][1], q_in, coef_ss, c1);
-        float* dst0 = abc[(u + 2) % 3][0];
-        float* dst1 = abc[(u + 2) % 3][1];
+        f2 cf[3];
+        ssim_coeffs2(mom[0], mom[1], mom[2], q_in, coef_ss, cf);
+        f2* dst = abc[(u + 2) % 3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const float lft = __shfl_up_sync(kFullMask, c1[j], 1), rgt = __shfl_down_sync(kFullMask, c0[j], 1);
-          const float mid = c0[j] + c1[j];
-          dst0[j] = mid + lft;
-          dst1[j] = mid + rgt;
+          const float lft = __shfl_up_sync(kFullMask, cf[j].y, 1), rgt = __shfl_down_sync(kFullMask, cf[j].x, 1);
+          const float mid = cf[j].x + cf[j].y;
+          dst[j] = make_float2(mid + lft, mid + rgt);
         }
       }
 
       const int p = r - 2;
       if (p >= sc.y0 && p < sc.y1 && pout) {
         const int sp = (u + 1) % 3;
-        float g[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float A = abc[0][k][0] + abc[1][k][0] + abc[2][k][0];
-          const float Bq = abc[0][k][1] + abc[1][k][1] + abc[2][k][1];
-          const float Cq = abc[0][k][2] + abc[1][k][2] + abc[2][k][2];
-          const float gy = fmaf(xy[sp][k][0], Cq, fmaf(2.0f * xy[sp][k][1], Bq, A));
-          g[k] = fmaf(gy, wl1[sp][k][0], wl1[sp][k][1]);
-        }
-        *reinterpret_cast<float2*>(gout + (unsigned)p * W) = make_float2(g[0], g[1]);
+        const f2 A = add2(add2(abc[0][0], abc[1][0]), abc[2][0]);
+        const f2 Bq = add2(add2(abc[0][1], abc[1][1]), abc[2][1]);
+        const f2 Cq = add2(add2(abc[0][2], abc[1][2]), abc[2][2]);
+        const f2 gy = fma2(xy[sp][0], Cq, fma2(add2(xy[sp][1], xy[sp][1]), Bq, A));
+        *reinterpret_cast<float2*>(gout + (unsigned)p * W) = fma2(gy, wl1[sp][0], wl1[sp][1]);
       }
     }
   }
@@ -583,7 +740,7 @@ photo_loss_bwd_pair_kernel(const __grid_constant__ PhotoParams P, const float* _
 }
 
 int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int B, int halo, bool bwd, int blocks_per_sm,
-                bool split = false, int ppl = 1) {
+                bool split = false, int ppl = 1, int strips_per_block = 0, int col_halo = -1) {
   UOF_REQUIRE(levels && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS, "photo_loss: nlevels must be 1..%d", UOF_MAX_LEVELS);
   UOF_REQUIRE(B > 0, "photo_loss: bad batch %d", B);
   int H[UOF_MAX_LEVELS], W[UOF_MAX_LEVELS];
@@ -598,7 +755,7 @@ int fill_params(PhotoParams& P, const uof_photo_level* levels, int nlevels, int 
   }
   // split backward: one block per strip; fused backward: two grid rows (directions) of 4-warp blocks
   UOF_REQUIRE(build_strip_table(P.T, H, W, nlevels, B, halo, (bwd && !split) ? 2 : 1, blocks_per_sm,
-                                split ? 1 : kWarpsPerBlock, ppl) > 0,
+                                strips_per_block > 0 ? strips_per_block : (split ? 1 : kWarpsPerBlock), ppl, col_halo) > 0,
               "photo_loss: problem too large");
   return UOF_OK;
 }
@@ -612,10 +769,26 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
                                   float* loss_ssim, uof_stream_t stream_) {
   UOF_REQUIRE(sums && loss_pixel && loss_ssim, "photo_loss_fwd: null output");
   PhotoParams P;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  bool pair_ok = levels != nullptr && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS && getenv("UOF_PHOTO_FWD_NO_PAIR") == nullptr;
+  for (int l = 0; pair_ok && l < nlevels; ++l) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(levels[l].img) | reinterpret_cast<uintptr_t>(levels[l].warped_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].warped_r) | reinterpret_cast<uintptr_t>(levels[l].weight_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].weight_r) | reinterpret_cast<uintptr_t>(levels[l].diff_l) |
+                           reinterpret_cast<uintptr_t>(levels[l].diff_r);
+    pair_ok = levels[l].W % 2 == 0 && levels[l].W >= 2 && (bits & 7u) == 0;
+  }
+  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
+  if (pair_ok) {      // direction-split pixel-pair kernel: two warps (directions) per strip, two strips per block
+    static const int occ_pair = resident_blocks(photo_loss_fwd_pair_kernel, kWarpsPerBlock * 32);
+    if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ_pair, false, 2, kWarpsPerBlock / 2, 2)) return rc;
+    photo_loss_fwd_pair_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock / 2), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
+    photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
+    count_launch(2);
+    return check_launch("photo_loss_fwd (pair)");
+  }
   static const int occ = resident_blocks(photo_loss_fwd_kernel, kWarpsPerBlock * 32);
   if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ)) return rc;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
   photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
