@@ -770,7 +770,8 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
   UOF_REQUIRE(sums && loss_pixel && loss_ssim, "photo_loss_fwd: null output");
   PhotoParams P;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  bool pair_ok = levels != nullptr && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS && getenv("UOF_PHOTO_FWD_NO_PAIR") == nullptr;
+  static const bool no_fwd_pair = getenv("UOF_PHOTO_FWD_NO_PAIR") != nullptr;
+  bool pair_ok = levels != nullptr && nlevels >= 1 && nlevels <= UOF_MAX_LEVELS && !no_fwd_pair;
   for (int l = 0; pair_ok && l < nlevels; ++l) {
     const uintptr_t bits = reinterpret_cast<uintptr_t>(levels[l].img) | reinterpret_cast<uintptr_t>(levels[l].warped_l) |
                            reinterpret_cast<uintptr_t>(levels[l].warped_r) | reinterpret_cast<uintptr_t>(levels[l].weight_l) |
