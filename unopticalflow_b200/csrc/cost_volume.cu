@@ -278,6 +278,7 @@ extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
   UOF_REQUIRE(out_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_fwd: out_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = 0;
+  if (cv::fwd_small(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
   if (cv::fwd_tma(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);

@@ -13,11 +13,25 @@ constexpr int DYG = 3;                 // displacement rows per thread
 constexpr int NGROUP = ND / DYG;       // 3 thread groups over dy
 constexpr int NT = 192;                // threads per CTA: 64 pixel quads x 3 dy-groups (every tile shape has 256 px)
 
-// split the channel loop so that small pyramid levels still put >= ~2 CTAs on every SM
+// Backward: split the channel loop of a tile over `s` CTAs (each writes its own output channels, no atomics) so that small
+// pyramid levels still fill the 148 SMs.  The split is chosen by a wave model, not just "enough CTAs": 2 CTAs are
+// resident per SM, a launch costs waves(ctas * s) x (slabs per CTA + prologue), the prologue (108 coefficient gathers per
+// thread, barrier init, first TMA round trip) being worth ~1.5 slabs.  The old rule (smallest s with ctas * s >= 296)
+// put the 16x52 / 8x26 / 4x13 levels at 384 / 320 / 320 CTAs = two waves of which the second is nearly empty.
 inline int pick_split(long long ctas, int nchunks) {
-  int s = 1;
-  while (ctas * s < 2 * kNumSMs && s < nchunks) ++s;
-  return s;
+  const long long slots = 2ll * kNumSMs;
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= nchunks; ++s) {
+    const long long waves = (ctas * s + slots - 1) / slots;
+    const int per = (nchunks + s - 1) / s;
+    const double cost = (double)waves * ((double)per + 1.5);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
 }
 
 // Forward split-K goes through fp32 atomics into a zeroed output, which is expensive (measured: the 32x104 level takes
@@ -28,6 +42,11 @@ inline int pick_ksplit_atomic(long long ctas, int nchunks) {
   if (s < 1) s = 1;
   return s < nchunks ? s : nchunks;
 }
+
+// Smallest pyramid levels (<= 64 pixel quads per image): one CTA per (image, displacement row), no split-K atomics.
+// Returns false when the level is not small (or UOF_CV_NO_SMALL is set); otherwise launches and stores the status in *rc.
+bool fwd_small(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
+               cudaStream_t stream, int* rc);
 
 // TMA + mbarrier implementations.  Return false when the TMA path does not apply (W % 4 != 0, unaligned
 // pointers, no driver entry point, UOF_DISABLE_TMA=1); otherwise launch and store the status in *rc.
