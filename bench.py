@@ -153,6 +153,9 @@ def algorithmic_bytes(name, args):
     if name == 'uof_bias_lrelu_fwd':            # read + write the activation in place
         B, C, H, W = args[2:6]
         return 8 * B * C * H * W
+    if name == 'uof_bias_lrelu_bwd2':           # read g1 (+ g2) and y, write gx
+        B, C, H, W = (int(v) for v in args[7:11])
+        return (4 if args[2] else 3) * 4 * B * C * H * W
     if name == 'uof_bias_lrelu_bwd':            # read gout and y, write gx
         B, C, H, W = args[4:8]
         return 12 * B * C * H * W
@@ -177,6 +180,8 @@ class KernelObserver:
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))
             if name == 'uof_warp_bwd':
                 key += '+gx' if args[3].value else ''
+        elif name == 'uof_bias_lrelu_bwd2':      # same key as the one-gradient form, '+g2' when two gradients are summed
+            key = 'uof_bias_lrelu_bwd[%s]%s' % ('x'.join(str(int(d)) for d in args[7:11]), '+g2' if args[2] else '')
         elif name.startswith('uof_bias_lrelu'):
             dims = args[2:6] if name.endswith('fwd') else args[4:8]
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))

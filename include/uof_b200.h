@@ -168,6 +168,12 @@ int uof_bias_lrelu_fwd(float* y, const float* bias, int B, int C, int H, int W, 
 /* y = the post-activation tensor of the forward pass; gx (B,C,H,W) overwritten, gbias (C) zero-filled then accumulated. */
 int uof_bias_lrelu_bwd(const float* gout, const float* y, float* gx, float* gbias, int B, int C, int H, int W,
                        float slope, uof_stream_t stream);
+/* Same with the incoming gradient given as g1 (+ g2, may be NULL): (B,C,H,W) views that are dense inside a sample and
+ * have an arbitrary batch stride (in floats) -- e.g. channel slices of torch.cat gradients -- summed on the fly, so the
+ * two consumers of a decoder activation (next convolution and concat, pwc_tf.py:119-131) need no separate add/copy. */
+int uof_bias_lrelu_bwd2(const float* g1, long long g1_batch_stride, const float* g2, long long g2_batch_stride,
+                        const float* y, float* gx, float* gbias, int B, int C, int H, int W, float slope,
+                        uof_stream_t stream);
 
 /* a12: forward splat ("transformerFwd").  NOT in the reference.
  * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;

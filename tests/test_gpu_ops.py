@@ -81,6 +81,41 @@ def test_conv_block_fused_bias_lrelu(U, cin, cout, h, w, stride, dil):
         assert_close(a, b, 1e-5, 'conv block grad ' + what)
 
 
+@pytest.mark.parametrize('h,w', [(16, 24), (13, 7)])
+def test_conv_block_forked_activation(U, h, w):
+    """fork=True hands the activation out twice (one tensor per consumer, same storage); the fused backward receives the
+    two gradients separately -- one of them a batch-strided channel slice of a torch.cat gradient, as in the decoder's
+    dense block (pwc_tf.py:113-118) -- and must give the gradients of the plain two-consumer graph."""
+    import torch.nn as nn
+    from unopticalflow_b200.networks.structures import conv
+    torch.manual_seed(5)
+    blk = conv(6, 8).cuda()
+    nxt = nn.Conv2d(8, 4, 3, padding=1).cuda()
+    ref = nn.Sequential(nn.Conv2d(6, 8, 3, 1, 1), nn.LeakyReLU(0.1)).cuda()
+    ref.load_state_dict(blk.state_dict())
+    x, z = torch.randn(2, 6, h, w, device='cuda'), torch.randn(2, 5, h, w, device='cuda')
+    ct1, ct2 = torch.randn(2, 4, h, w, device='cuda'), torch.randn(2, 13, h, w, device='cuda')
+
+    def loss(a_for_conv, a_for_cat):
+        return (nxt(a_for_conv) * ct1).sum() + (torch.cat((z, a_for_cat), 1) * ct2).sum()
+
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = blk(xa, fork=True)
+    assert ya.data_ptr() == yb.data_ptr()
+    ga = torch.autograd.grad(loss(ya, yb), [xa, blk[0].weight, blk[0].bias])
+    yr = ref(xb)
+    gb = torch.autograd.grad(loss(yr, yr), [xb, ref[0].weight, ref[0].bias])
+    for a, b, what in zip(ga, gb, ('input', 'weight', 'bias')):
+        assert_close(a, b, 1e-5, 'forked conv block grad ' + what)
+    # one consumer only: the other gradient is None
+    xc = x.clone().requires_grad_(True)
+    yc, _unused = blk(xc, fork=True)
+    gc = torch.autograd.grad((yc * ct1[:, :1]).sum(), [xc])[0]
+    xd = x.clone().requires_grad_(True)
+    gd = torch.autograd.grad((ref(xd) * ct1[:, :1]).sum(), [xd])[0]
+    assert_close(gc, gd, 1e-5, 'forked conv block, single consumer')
+
+
 @pytest.mark.parametrize('shape', [(2, 32, 16, 24), (2, 5, 7, 9), (1, 64, 32, 104)])
 def test_corr_concat_matches_cat(U, shape):
     """Decoder glue fusion: cat((corr, c1, up), 1) with the cost volume written in place, values and grads."""

@@ -50,24 +50,34 @@ bias_lrelu_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, int
   }
 }
 
-template <bool VEC4>
+// gout = g1 (+ g2): the incoming gradient may arrive as TWO tensors.  In the decoder every activation feeds two consumers
+// (the next convolution and a torch.cat, pwc_tf.py:119-131); autograd would add the two gradients with a strided
+// elementwise kernel (they are channel slices of cat gradients: dense inside a sample, batch stride of the cat) and hand
+// the sum over -- 36 launches / 0.55 ms per step plus 14 .contiguous() copies (ncu launch list, round 2).  Here both
+// arrive as they are (`bs1`, `bs2` = batch strides in floats) and are summed on the fly.
+template <bool VEC4, bool TWO>
 __global__ void __launch_bounds__(kThreads)
-bias_lrelu_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ y, float* __restrict__ gx,
-                      float* __restrict__ gbias, int C, int plane, float slope) {
+bias_lrelu_bwd_kernel(const float* __restrict__ g1, long long bs1, const float* __restrict__ g2, long long bs2,
+                      const float* __restrict__ y, float* __restrict__ gx, float* __restrict__ gbias, int C, int plane,
+                      float slope) {
   const int c = blockIdx.y, b = blockIdx.z;
   const size_t base = ((size_t)b * C + c) * plane;
+  const float* g1p = g1 + (size_t)b * bs1 + (size_t)c * plane;
+  const float* g2p = TWO ? g2 + (size_t)b * bs2 + (size_t)c * plane : nullptr;
   float acc = 0.0f;
   if (VEC4) {
     const int n4 = plane >> 2;
-    const float4* g4 = reinterpret_cast<const float4*>(gout + base);
+    const float4* g4 = reinterpret_cast<const float4*>(g1p);
+    const float4* h4 = reinterpret_cast<const float4*>(g2p);
     const float4* y4 = reinterpret_cast<const float4*>(y + base);
     float4* o4 = reinterpret_cast<float4*>(gx + base);
-    float4 g[ITER], v[ITER];
+    float4 g[ITER], h[ITER], v[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {      // all loads first
       const int i = (blockIdx.x * ITER + it) * kThreads + threadIdx.x;
       if (i < n4) {
         g[it] = __ldg(g4 + i);
+        if (TWO) h[it] = __ldg(h4 + i);
         v[it] = __ldg(y4 + i);
       }
     }
@@ -75,11 +85,13 @@ bias_lrelu_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ 
     for (int it = 0; it < ITER; ++it) {
       const int i = (blockIdx.x * ITER + it) * kThreads + threadIdx.x;
       if (i < n4) {
+        float4 t = g[it];
+        if (TWO) { t.x += h[it].x; t.y += h[it].y; t.z += h[it].z; t.w += h[it].w; }
         float4 r;
-        r.x = v[it].x > 0.0f ? g[it].x : g[it].x * slope;
-        r.y = v[it].y > 0.0f ? g[it].y : g[it].y * slope;
-        r.z = v[it].z > 0.0f ? g[it].z : g[it].z * slope;
-        r.w = v[it].w > 0.0f ? g[it].w : g[it].w * slope;
+        r.x = v[it].x > 0.0f ? t.x : t.x * slope;
+        r.y = v[it].y > 0.0f ? t.y : t.y * slope;
+        r.z = v[it].z > 0.0f ? t.z : t.z * slope;
+        r.w = v[it].w > 0.0f ? t.w : t.w * slope;
         o4[i] = r;
         acc += (r.x + r.y) + (r.z + r.w);
       }
@@ -89,7 +101,8 @@ bias_lrelu_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ 
     for (int it = 0; it < ITER * 4; ++it) {
       const int i = (blockIdx.x * ITER * 4 + it) * kThreads + threadIdx.x;
       if (i < plane) {
-        const float gv = __ldg(gout + base + i);
+        float gv = __ldg(g1p + i);
+        if (TWO) gv += __ldg(g2p + i);
         const float r = __ldg(y + base + i) > 0.0f ? gv : gv * slope;
         gx[base + i] = r;
         acc += r;
@@ -131,18 +144,29 @@ extern "C" int uof_bias_lrelu_fwd(float* y, const float* bias, int B, int C, int
   return check_launch("bias_lrelu_fwd");
 }
 
-extern "C" int uof_bias_lrelu_bwd(const float* gout, const float* y, float* gx, float* gbias, int B, int C, int H, int W,
-                                  float slope, uof_stream_t stream_) {
-  if (int rc = check("bias_lrelu_bwd", gout, y, B, C, H, W)) return rc;
+extern "C" int uof_bias_lrelu_bwd2(const float* g1, long long g1_batch_stride, const float* g2, long long g2_batch_stride,
+                                   const float* y, float* gx, float* gbias, int B, int C, int H, int W, float slope,
+                                   uof_stream_t stream_) {
+  if (int rc = check("bias_lrelu_bwd", g1, y, B, C, H, W)) return rc;
   UOF_REQUIRE(gx && gbias, "bias_lrelu_bwd: null output");
   const int plane = H * W;
-  const bool v4 = (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(y) |
-                                        reinterpret_cast<uintptr_t>(gx)) & 15u) == 0;
+  UOF_REQUIRE(g1_batch_stride >= (long long)C * plane && (!g2 || g2_batch_stride >= (long long)C * plane),
+              "bias_lrelu_bwd: gradient batch stride smaller than a sample");
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(y) |
+                         reinterpret_cast<uintptr_t>(gx);
+  const bool v4 = (plane % 4 == 0) && (bits & 15u) == 0 && g1_batch_stride % 4 == 0 && (!g2 || g2_batch_stride % 4 == 0);
   dim3 grid(ceil_div(v4 ? plane / 4 : ceil_div(plane, 4), kThreads * ITER), C, B);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(gbias, 0, (size_t)C * sizeof(float), stream));
-  if (v4) bias_lrelu_bwd_kernel<true><<<grid, kThreads, 0, stream>>>(gout, y, gx, gbias, C, plane, slope);
-  else bias_lrelu_bwd_kernel<false><<<grid, kThreads, 0, stream>>>(gout, y, gx, gbias, C, plane, slope);
+#define UOF_BWD(V, T) bias_lrelu_bwd_kernel<V, T><<<grid, kThreads, 0, stream>>>(g1, g1_batch_stride, g2, g2_batch_stride, y, gx, gbias, C, plane, slope)
+  if (v4) { if (g2) UOF_BWD(true, true); else UOF_BWD(true, false); }
+  else { if (g2) UOF_BWD(false, true); else UOF_BWD(false, false); }
+#undef UOF_BWD
   count_launch();
   return check_launch("bias_lrelu_bwd");
+}
+
+extern "C" int uof_bias_lrelu_bwd(const float* gout, const float* y, float* gx, float* gbias, int B, int C, int H, int W,
+                                  float slope, uof_stream_t stream_) {
+  return uof_bias_lrelu_bwd2(gout, (long long)C * H * W, nullptr, 0, y, gx, gbias, B, C, H, W, slope, stream_);
 }

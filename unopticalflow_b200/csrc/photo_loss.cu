@@ -779,17 +779,18 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
                            reinterpret_cast<uintptr_t>(levels[l].diff_r);
     pair_ok = levels[l].W % 2 == 0 && levels[l].W >= 2 && (bits & 7u) == 0;
   }
-  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   if (pair_ok) {      // direction-split pixel-pair kernel: two warps (directions) per strip, two strips per block
     static const int occ_pair = resident_blocks(photo_loss_fwd_pair_kernel, kWarpsPerBlock * 32);
     if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ_pair, false, 2, kWarpsPerBlock / 2, 2)) return rc;
+    UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
     photo_loss_fwd_pair_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock / 2), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
     photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
     count_launch(2);
     return check_launch("photo_loss_fwd (pair)");
   }
   static const int occ = resident_blocks(photo_loss_fwd_kernel, kWarpsPerBlock * 32);
-  if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ)) return rc;
+  if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ)) return rc;      // argument validation before any CUDA call
+  UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
   photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
   photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);

@@ -92,8 +92,11 @@ class Model_flow(nn.Module):
         imgl, img, imgr = inputs[:, :, :H], inputs[:, :, H:2 * H], inputs[:, :, 2 * H:3 * H]
 
         feats = self.fpyramid(torch.cat((imgl, img, imgr), 0))                      # one 3B encoder pass
-        f1 = [torch.cat((f[B:2 * B], f[B:2 * B]), 0) for f in feats]                 # [centre ; centre]
-        f2 = [torch.cat((f[:B], f[2 * B:]), 0) for f in feats]                       # [left   ; right ]
+        # split (not three slices): its backward is ONE concatenation of the three gradients instead of three
+        # zero-filled full-size tensors plus adds
+        parts = [f.split(B, 0) for f in feats]                                       # (left, centre, right)
+        f1 = [torch.cat((c, c), 0) for _, c, _ in parts]                             # [centre ; centre]
+        f2 = [torch.cat((l, r), 0) for l, _, r in parts]                             # [left   ; right ]
         flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
 
         pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)                  # one launch, triplet read in place

@@ -27,10 +27,11 @@ class ConvLReLU(nn.Sequential):
     bias + LeakyReLU kernel (in place), whose backward also produces the bias gradient.  Like every other operator of
     the package it has no CPU path."""
 
-    def forward(self, x):
+    def forward(self, x, fork=False):
+        """`fork=True`: return the activation twice, one tensor per consumer (ops._BiasLeakyReLU)."""
         cv, act = self[0], self[1]
         y = F.conv2d(x, cv.weight, None, cv.stride, cv.padding, cv.dilation, cv.groups)
-        return ops.bias_leaky_relu_(y, cv.bias, act.negative_slope)
+        return ops.bias_leaky_relu_(y, cv.bias, act.negative_slope, fork)
 
 
 def conv(in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1):
@@ -50,9 +51,13 @@ class FeaturePyramid(nn.Module):
 
     def forward(self, img):
         feats, t = [], img
+        last = len(_ENCODER) - 1
         for k in range(len(_ENCODER)):
-            t = getattr(self, 'conv%d' % (2 * k + 2))(getattr(self, 'conv%d' % (2 * k + 1))(t))
-            feats.append(t)
+            # every level but the last feeds the next level AND the decoder: fork (see ConvLReLU.forward)
+            fork = k < last
+            out = getattr(self, 'conv%d' % (2 * k + 2))(getattr(self, 'conv%d' % (2 * k + 1))(t), fork=fork)
+            t, f = out if fork else (out, out)
+            feats.append(f)
         return tuple(feats)
 
 
@@ -89,12 +94,14 @@ class PWC_tf(nn.Module):
         return ops.warp_flow(x, flow, use_mask=False, align_corners=self.align_corners)
 
     def _level(self, lvl, x):
-        x0 = getattr(self, 'conv%d_0' % lvl)(x)
-        x1 = getattr(self, 'conv%d_1' % lvl)(x0)
-        x2 = getattr(self, 'conv%d_2' % lvl)(torch.cat((x0, x1), 1))
-        x3 = getattr(self, 'conv%d_3' % lvl)(torch.cat((x1, x2), 1))
-        x4 = getattr(self, 'conv%d_4' % lvl)(torch.cat((x2, x3), 1))
-        return getattr(self, 'predict_flow%d' % lvl)(torch.cat((x3, x4), 1)), x4
+        # pwc_tf.py:113-118 etc.; every activation has two consumers, hence the forks (one tensor per consumer, so that
+        # the fused LeakyReLU backward receives the two gradients separately and sums them itself)
+        x0a, x0b = getattr(self, 'conv%d_0' % lvl)(x, fork=True)
+        x1a, x1b = getattr(self, 'conv%d_1' % lvl)(x0a, fork=True)
+        x2a, x2b = getattr(self, 'conv%d_2' % lvl)(torch.cat((x0b, x1a), 1), fork=True)
+        x3a, x3b = getattr(self, 'conv%d_3' % lvl)(torch.cat((x1b, x2a), 1), fork=True)
+        x4a, x4b = getattr(self, 'conv%d_4' % lvl)(torch.cat((x2b, x3a), 1), fork=True)
+        return getattr(self, 'predict_flow%d' % lvl)(torch.cat((x3b, x4a), 1)), x4b
 
     def forward(self, feature_list_1, feature_list_2, img_hw):
         flows, up, x4 = {}, None, None

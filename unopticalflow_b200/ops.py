@@ -465,12 +465,22 @@ def flow_consis_loss(fwd_flows, bwd_flows, weights_fwd, num_scales=3):
 
 
 # ------------------------------------------------------------------------------------ a11 glue
+def _sample_dense(g, C, H, W):
+    """(B,C,H,W) view that is dense inside a sample (any batch stride): what torch.cat's backward hands out."""
+    return g.stride(3) == 1 and g.stride(2) == W and g.stride(1) == H * W and g.stride(0) >= C * H * W
+
+
 class _BiasLeakyReLU(torch.autograd.Function):
     """y <- lrelu(y + bias[c]) in place on a fresh convolution output; backward fuses LeakyReLU-backward with the bias
-    gradient reduction (glue around the kept-PyTorch convolutions, net_utils.py:7-11)."""
+    gradient reduction (glue around the kept-PyTorch convolutions, net_utils.py:7-11).
+
+    `fork=True` returns the activation TWICE (two tensors on the same storage), one for each of its two consumers in the
+    decoder's dense block (next convolution and torch.cat, pwc_tf.py:119-131).  Autograd then delivers the two
+    gradients separately and the backward kernel sums them on the fly -- channel slices of cat gradients included, through
+    their batch stride -- instead of autograd's strided add kernel plus a .contiguous() copy per activation."""
 
     @staticmethod
-    def forward(ctx, y, bias, slope):
+    def forward(ctx, y, bias, slope, fork):
         assert y.is_contiguous()
         B, C, H, W = y.shape
         with torch.cuda.device_of(y):
@@ -478,26 +488,37 @@ class _BiasLeakyReLU(torch.autograd.Function):
         ctx.mark_dirty(y)
         ctx.save_for_backward(y)
         ctx.slope = float(slope)
+        if fork:
+            return y, y.detach()
         return y
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, g1, g2=None):
         (y,) = ctx.saved_tensors
         B, C, H, W = y.shape
-        gout = gout.contiguous()
+        if g1 is None:
+            g1, g2 = g2, None
+        if g1 is None:
+            return None, None, None, None
+        if not _sample_dense(g1, C, H, W):
+            g1 = g1.contiguous()
+        if g2 is not None and not _sample_dense(g2, C, H, W):
+            g2 = g2.contiguous()
         gx = torch.empty_like(y)
         gbias = torch.empty(C, device=y.device, dtype=torch.float32)
         with torch.cuda.device_of(y):
-            _lib.call('uof_bias_lrelu_bwd', _p(gout), _p(y), _p(gx), _p(gbias), B, C, H, W, ctx.slope, _stream(y))
-        return gx, gbias, None
+            _lib.call('uof_bias_lrelu_bwd2', _p(g1), g1.stride(0), _p(g2) if g2 is not None else None,
+                      g2.stride(0) if g2 is not None else 0, _p(y), _p(gx), _p(gbias), B, C, H, W, ctx.slope, _stream(y))
+        return gx, gbias, None, None
 
 
-def bias_leaky_relu_(y: torch.Tensor, bias: torch.Tensor, negative_slope: float = 0.1) -> torch.Tensor:
-    """In-place lrelu(y + bias[None,:,None,None]); `y` must be a freshly produced (non-leaf) contiguous NCHW tensor."""
+def bias_leaky_relu_(y: torch.Tensor, bias: torch.Tensor, negative_slope: float = 0.1, fork: bool = False):
+    """In-place lrelu(y + bias[None,:,None,None]); `y` must be a freshly produced (non-leaf) contiguous NCHW tensor.
+    `fork=True` returns two tensors on the same storage for an activation with two consumers (see _BiasLeakyReLU)."""
     _require_cuda(y, bias)
     if not y.is_contiguous():
         y = y.contiguous()
-    return _BiasLeakyReLU.apply(y, bias.contiguous(), negative_slope)
+    return _BiasLeakyReLU.apply(y, bias.contiguous(), negative_slope, bool(fork))
 
 
 # ------------------------------------------------------------------------------------------ a9
