@@ -160,6 +160,13 @@ int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, cons
 int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, long long stride_c,
                     long long stride_h, float* const* outs /* host array of nlevels-1 device pointers */,
                     int nlevels, int nimg, int B, int C, int H, int W, uof_stream_t stream);
+/* Same, with the outputs stacked by SLOT: input image i goes to slot[i] (host array, a permutation of 0..nimg-1; NULL =
+ * identity), and an optional dense (nimg,B,C,H,W) copy `out0` of level 0 in the same order.  Model_flow.forward orders
+ * the triplet as [left; right; centre], so that the encoder's 3B batch and the [left; right] sources of the image warps
+ * (model_flow_paper.py:206-209,233-235) are plain views instead of torch.cat copies.  Needs H, W % 4 == 0, nlevels <= 3. */
+int uof_img_pyramid_stacked(const float* img, long long stride_img, long long stride_b, long long stride_c,
+                            long long stride_h, float* out0, const int* slot, float* const* outs, int nlevels, int nimg,
+                            int B, int C, int H, int W, uof_stream_t stream);
 
 /* a11 glue: fused bias + LeakyReLU after a bias-free convolution.  Replaces the bias epilogue + LeakyReLU
  * of conv() (net_utils.py:7-11) forward, and LeakyReLU-backward + bias-gradient reduction backward.

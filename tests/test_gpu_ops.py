@@ -524,6 +524,22 @@ def test_img_pyramid(U, shape):
         assert_close(a, b, 1e-5)
 
 
+def test_img_pyramid_triplet_stacked(U):
+    """One launch: all levels of the three images stacked as [left; right; centre], level 0 as a dense copy (the encoder's
+    batch and the warp sources are views of it); must equal the per-image pyramids.  Shapes off the fast path return None."""
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 2, 32, 48
+    trip = torch.rand(B, 3, 3 * H, W, generator=g)
+    stk = U.ops.img_pyramid_triplet_stacked(trip.cuda(), 3)
+    assert stk is not None and [tuple(t.shape) for t in stk] == [(3, B, 3, H, W), (3, B, 3, H // 2, W // 2), (3, B, 3, H // 4, W // 4)]
+    for slot, k in enumerate((0, 2, 1)):           # slots: left, right, centre <- input images 0, 2, 1
+        ref = O.img_pyramid(trip[:, :, k * H:(k + 1) * H], 3)
+        for s in range(3):
+            assert_close(stk[s][slot], ref[s], 1e-6, 'slot %d level %d' % (slot, s))
+    assert torch.equal(stk[0][0].cpu(), trip[:, :, :H])                            # level 0 is an exact copy
+    assert U.ops.img_pyramid_triplet_stacked(torch.rand(1, 3, 3 * 30, 50).cuda(), 3) is None
+
+
 # -------------------------------------------------------------------------------------- a12/a13
 @pytest.mark.parametrize('B,H,W,sigma', [(2, 9, 11, 2.0), (1, 32, 50, 8.0), (2, 64, 208, 1.0)])
 def test_splat_targets_bit_exact_and_range_map(U, B, H, W, sigma):

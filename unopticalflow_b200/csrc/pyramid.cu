@@ -18,6 +18,8 @@ struct PyrParams {
   long long begin[UOF_MAX_LEVELS + 1];
   int nout, nimg, B, C, H, W;
   long long si, sb, sc, sh;            // element strides: image, batch, channel, row
+  float* out0;                         // optional dense (nimg, B, C, H, W) copy of level 0 (pow2 kernel only)
+  int slot[4];                         // output slot of input image i (a permutation of 0..nimg-1)
 };
 
 __global__ void __launch_bounds__(256) pyramid_generic_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
@@ -48,13 +50,20 @@ __global__ void __launch_bounds__(256) pyramid_pow2_kernel(const __grid_constant
   const long long total = (long long)P.nimg * P.B * P.C * H4 * W4;
   if (t >= total) return;
   const int bx = (int)(t % W4), by = (int)((t / W4) % H4);
-  const long long plane_id = t / ((long long)W4 * H4);          // (im*B + b)*C + c
+  long long plane_id = t / ((long long)W4 * H4);                // (im*B + b)*C + c
   const int c = (int)(plane_id % P.C);
   const int b = (int)((plane_id / P.C) % P.B), im = (int)(plane_id / ((long long)P.C * P.B));
   const float* src = img + im * P.si + b * P.sb + c * P.sc + (long long)(4 * by) * P.sh + 4 * bx;
   float4 r[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) r[k] = __ldg(reinterpret_cast<const float4*>(src + k * P.sh));
+  // outputs are stacked by slot, not by input image: lets the caller order the triplet as [left; right; centre]
+  plane_id = ((long long)P.slot[im] * P.B + b) * P.C + c;
+  if (P.out0) {        // dense copy of level 0 in the same stacked order (the encoder's 3B batch, the [l;r] warp sources)
+    float* o0 = P.out0 + plane_id * ((long long)P.H * P.W) + (long long)(4 * by) * P.W + 4 * bx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(o0 + (long long)k * P.W) = r[k];
+  }
   // level 1: 2x2 means, accumulated row-major like adaptive_avg_pool2d
   const float a00 = ((r[0].x + r[0].y) + r[1].x + r[1].y) * 0.25f, a01 = ((r[0].z + r[0].w) + r[1].z + r[1].w) * 0.25f;
   const float a10 = ((r[2].x + r[2].y) + r[3].x + r[3].y) * 0.25f, a11 = ((r[2].z + r[2].w) + r[3].z + r[3].w) * 0.25f;
@@ -75,9 +84,9 @@ __global__ void __launch_bounds__(256) pyramid_pow2_kernel(const __grid_constant
 
 using namespace uof;
 
-extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, long long stride_c,
-                               long long stride_h, float* const* outs, int nlevels, int nimg, int B, int C, int H, int W,
-                               uof_stream_t stream_) {
+extern "C" int uof_img_pyramid_stacked(const float* img, long long stride_img, long long stride_b, long long stride_c,
+                                       long long stride_h, float* out0, const int* slot, float* const* outs, int nlevels,
+                                       int nimg, int B, int C, int H, int W, uof_stream_t stream_) {
   UOF_REQUIRE(img && outs, "img_pyramid: null pointer");
   UOF_REQUIRE(nlevels >= 2 && nlevels <= UOF_MAX_LEVELS + 1, "img_pyramid: nlevels must be 2..%d", UOF_MAX_LEVELS + 1);
   UOF_REQUIRE(nimg > 0 && B > 0 && C > 0 && H > 0 && W > 0, "img_pyramid: bad shape");
@@ -86,6 +95,10 @@ extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long
   P.nout = nlevels - 1;
   P.nimg = nimg; P.B = B; P.C = C; P.H = H; P.W = W;
   P.si = stride_img; P.sb = stride_b; P.sc = stride_c; P.sh = stride_h;
+  P.out0 = out0;
+  UOF_REQUIRE(!slot || nimg <= 4, "img_pyramid: a slot permutation supports at most 4 images");
+  for (int i = 0; i < 4; ++i) P.slot[i] = (slot && i < nimg) ? slot[i] : i;
+  for (int i = 0; slot && i < nimg; ++i) UOF_REQUIRE(slot[i] >= 0 && slot[i] < nimg, "img_pyramid: bad slot %d", slot[i]);
   long long total = 0;
   for (int l = 0; l < P.nout; ++l) {
     const int s = l + 1;
@@ -99,7 +112,9 @@ extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long
   P.begin[P.nout] = total;
   const bool strides_ok = (stride_img % 4 == 0) && (stride_b % 4 == 0) && (stride_c % 4 == 0) && (stride_h % 4 == 0) &&
                           (reinterpret_cast<uintptr_t>(img) & 15u) == 0 && (reinterpret_cast<uintptr_t>(outs[0]) & 7u) == 0;
-  if (H % 4 == 0 && W % 4 == 0 && P.nout <= 2 && strides_ok) {
+  const bool fast = H % 4 == 0 && W % 4 == 0 && P.nout <= 2 && strides_ok && (!out0 || (reinterpret_cast<uintptr_t>(out0) & 15u) == 0);
+  UOF_REQUIRE(fast || (!out0 && !slot), "img_pyramid: the stacked level-0 copy / slot order need H, W %% 4 == 0, <= 3 levels and 16-byte aligned strides");
+  if (fast) {
     const long long threads = (long long)nimg * B * C * (H / 4) * (W / 4);
     pyramid_pow2_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, stream>>>(P, img);
   } else {
@@ -107,4 +122,11 @@ extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long
   }
   count_launch();
   return check_launch("img_pyramid");
+}
+
+extern "C" int uof_img_pyramid(const float* img, long long stride_img, long long stride_b, long long stride_c,
+                               long long stride_h, float* const* outs, int nlevels, int nimg, int B, int C, int H, int W,
+                               uof_stream_t stream_) {
+  return uof_img_pyramid_stacked(img, stride_img, stride_b, stride_c, stride_h, nullptr, nullptr, outs, nlevels, nimg, B, C, H,
+                                 W, stream_);
 }

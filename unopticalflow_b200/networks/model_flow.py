@@ -89,19 +89,29 @@ class Model_flow(nn.Module):
         assert inputs.shape[1] == 3
         B, H, W = inputs.shape[0], int(inputs.shape[2] / 3), inputs.shape[3]
         S = self.num_scales
-        imgl, img, imgr = inputs[:, :, :H], inputs[:, :, H:2 * H], inputs[:, :, 2 * H:3 * H]
-
-        feats = self.fpyramid(torch.cat((imgl, img, imgr), 0))                      # one 3B encoder pass
-        # split (not three slices): its backward is ONE concatenation of the three gradients instead of three
-        # zero-filled full-size tensors plus adds
-        parts = [f.split(B, 0) for f in feats]                                       # (left, centre, right)
-        f1 = [torch.cat((c, c), 0) for _, c, _ in parts]                             # [centre ; centre]
-        f2 = [torch.cat((l, r), 0) for l, _, r in parts]                             # [left   ; right ]
+        stacked = ops.img_pyramid_triplet_stacked(inputs, S)
+        if stacked is not None:
+            # one launch: every pyramid level (level 0 as a dense copy) stacked as [left; right; centre], so the encoder's
+            # 3B batch and the [left; right] warp sources are views -- no torch.cat of the images anywhere
+            feats = self.fpyramid(stacked[0].view(3 * B, 3, H, W))                   # one 3B encoder pass
+            parts = [f.split(B, 0) for f in feats]                                   # (left, right, centre)
+            f1 = [torch.cat((c, c), 0) for _, _, c in parts]                         # [centre ; centre]
+            f2 = [torch.cat((l, r), 0) for l, r, _ in parts]                         # [left   ; right ]
+            pyr_c = [t[2] for t in stacked]
+            sources = [t[:2].reshape(2 * B, 3, t.shape[3], t.shape[4]) for t in stacked]
+        else:
+            imgl, img, imgr = inputs[:, :, :H], inputs[:, :, H:2 * H], inputs[:, :, 2 * H:3 * H]
+            feats = self.fpyramid(torch.cat((imgl, img, imgr), 0))
+            # split (not three slices): its backward is ONE concatenation of the three gradients instead of three
+            # zero-filled full-size tensors plus adds
+            parts = [f.split(B, 0) for f in feats]                                   # (left, centre, right)
+            f1 = [torch.cat((c, c), 0) for _, c, _ in parts]
+            f2 = [torch.cat((l, r), 0) for l, _, r in parts]
+            pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)              # one launch, triplet read in place
+            sources = [torch.cat((pyr_l[s], pyr_r[s]), 0) for s in range(S)]
         flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
-
-        pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)                  # one launch, triplet read in place
-        warped = [ops.warp_flow(torch.cat((pyr_l[s], pyr_r[s]), 0), flows[s], use_mask=True,
-                                align_corners=self.align_corners) for s in range(S)]  # [from_l ; from_r]
+        warped = [ops.warp_flow(sources[s], flows[s], use_mask=True, align_corners=self.align_corners)
+                  for s in range(S)]                                                  # [from_l ; from_r]
 
         loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
         smooth = ops.flow_smooth_loss(flows, pyr_c, S)                               # (2B,): [bwd ; fwd]

@@ -567,6 +567,31 @@ def img_pyramid_triplet(inputs: torch.Tensor, num_pyramid: int):
     return pyr[0], pyr[1], pyr[2], stacked
 
 
+TRIPLET_SLOTS = (0, 2, 1)        # input image (left, centre, right) -> slot in the stacked [left; right; centre] order
+
+
+def img_pyramid_triplet_stacked(inputs: torch.Tensor, num_pyramid: int):
+    """Like img_pyramid_triplet, but every level -- level 0 included, as a dense copy -- comes back as ONE (3,B,3,h,w)
+    tensor ordered [left; right; centre]: `stacked[0].view(3B,3,H,W)` is the encoder's batch and `stacked[s][:2]` viewed as
+    (2B,3,h,w) the [left; right] source of the image warps, with no torch.cat.  Returns None when the fast path does not
+    apply (H or W not a multiple of 4, more than 3 levels, unaligned input)."""
+    _require_cuda(inputs)
+    x = inputs.detach()
+    B, C, H3, W = x.shape
+    H = H3 // 3
+    if (x.stride(3) != 1 or H3 % 3 or H % 4 or W % 4 or not 2 <= num_pyramid <= 3 or x.data_ptr() % 16
+            or any(st % 4 for st in (H * x.stride(2), x.stride(0), x.stride(1), x.stride(2)))):
+        return None
+    lv0 = torch.empty((3, B, C, H, W), device=x.device)
+    lv = [torch.empty((3, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=x.device) for s in range(1, num_pyramid)]
+    ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
+    slots = (ctypes.c_int * 3)(*TRIPLET_SLOTS)
+    with torch.cuda.device_of(x):
+        _lib.call('uof_img_pyramid_stacked', _p(x), H * x.stride(2), x.stride(0), x.stride(1), x.stride(2), _p(lv0), slots, ptrs,
+                  num_pyramid, 3, B, C, H, W, _stream(x))
+    return [lv0] + lv
+
+
 # -------------------------------------------------------------------------------------- a12/a13
 class _Splat(torch.autograd.Function):
     @staticmethod
