@@ -182,6 +182,15 @@ int uof_bias_lrelu_bwd2(const float* g1, long long g1_batch_stride, const float*
                         const float* y, float* gx, float* gbias, int B, int C, int H, int W, float slope,
                         uof_stream_t stream);
 
+/* a11 glue: bilinear up-sampling (align_corners = False, ATen upsample_bilinear2d semantics) fused with a scale factor:
+ * out = scale * interpolate(in).  Replaces `F.interpolate(flow, scale_factor=2.0, mode='bilinear') * 2.0`
+ * (pwc_tf.py:119,132,144,157) and `F.interpolate(flow * 4.0, [h, w], mode='bilinear')` (pwc_tf.py:174-177).
+ * in: (planes,h,w), out: (planes,H,W), H >= h, W >= w.  The backward pass is a gather (no atomics). */
+int uof_upsample_bilinear_fwd(const float* in, float* out, int planes, int h, int w, int H, int W, float scale,
+                              uof_stream_t stream);
+int uof_upsample_bilinear_bwd(const float* gout, float* gin, int planes, int h, int w, int H, int W, float scale,
+                              uof_stream_t stream);
+
 /* a12: forward splat ("transformerFwd").  NOT in the reference.
  * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;
  * out: (B,H,W,C), zero-filled here then accumulated with warp-aggregated fp32 atomics. */

@@ -81,6 +81,27 @@ def test_conv_block_fused_bias_lrelu(U, cin, cout, h, w, stride, dil):
         assert_close(a, b, 1e-5, 'conv block grad ' + what)
 
 
+@pytest.mark.parametrize('shape,size,scale', [((2, 2, 4, 13), (8, 26), 2.0), ((3, 2, 16, 52), (64, 208), 4.0),
+                                              ((1, 3, 5, 7), (11, 20), 1.0), ((2, 2, 6, 6), (6, 6), 4.0)])
+def test_upsample_bilinear_scaled(U, shape, size, scale):
+    """Fused `F.interpolate(x, size, mode='bilinear') * scale` (pwc_tf.py:119,174-177) against ATen on the same GPU: values
+    and the gather-form gradient (ATen scatters with atomics), integer and non-integer ratios, identity size."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).cuda()
+    ct = torch.randn(shape[0], shape[1], *size, generator=g).cuda()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = U.ops.upsample_bilinear_scaled(xa, size, scale)
+    yb = torch.nn.functional.interpolate(xb * scale, list(size), mode='bilinear')
+    assert ya.shape == yb.shape
+    assert_close(ya, yb, 1e-6, 'upsample fwd')
+    ga, = torch.autograd.grad((ya * ct).sum(), [xa])
+    gb, = torch.autograd.grad((yb * ct).sum(), [xb])
+    assert_close(ga, gb, 1e-5, 'upsample bwd')
+    if scale == 2.0:     # the decoder's form: scale_factor=2.0, multiplied afterwards
+        yc = torch.nn.functional.interpolate(x, scale_factor=2.0, mode='bilinear') * 2.0
+        assert_close(ya, yc, 1e-6, 'x2 up-sampling vs the reference expression')
+
+
 @pytest.mark.parametrize('h,w', [(16, 24), (13, 7)])
 def test_conv_block_forked_activation(U, h, w):
     """fork=True hands the activation out twice (one tensor per consumer, same storage); the fused backward receives the

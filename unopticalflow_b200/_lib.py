@@ -61,6 +61,8 @@ SIGNATURES = {
     'uof_bias_lrelu_fwd': [_P, _P, _I, _I, _I, _I, _F, _P],
     'uof_bias_lrelu_bwd': [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     'uof_bias_lrelu_bwd2': [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    'uof_upsample_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
+    'uof_upsample_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
     'uof_img_pyramid': [_P, _LL, _LL, _LL, _LL, ctypes.POINTER(ctypes.c_void_p), _I, _I, _I, _I, _I, _I, _P],
     'uof_img_pyramid_stacked': [_P, _LL, _LL, _LL, _LL, _P, ctypes.POINTER(_I), ctypes.POINTER(ctypes.c_void_p), _I, _I, _I, _I, _I,
                                 _I, _P],

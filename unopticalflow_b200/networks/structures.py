@@ -118,10 +118,11 @@ class PWC_tf(nn.Module):
                 flow = res + up
             flows[lvl] = flow
             if lvl > 2:
-                up = F.interpolate(flow, scale_factor=2.0, mode='bilinear') * 2.0
+                up = ops.upsample_bilinear_scaled(flow, (2 * flow.shape[2], 2 * flow.shape[3]), 2.0)      # pwc_tf.py:119
         t = torch.cat((flows[2], x4), 1)
         for i in range(1, 7):
             t = getattr(self, 'dc_conv%d' % i)(t)
         flows[2] = flows[2] + self.dc_conv7(t)
         img_h, img_w = img_hw[0], img_hw[1]
-        return [F.interpolate(flows[2 + s] * 4.0, [img_h // 2 ** s, img_w // 2 ** s], mode='bilinear') for s in range(4)]
+        # pwc_tf.py:174-177: F.interpolate(flow * 4.0, size) -- the power-of-two scale commutes exactly with the interpolation
+        return [ops.upsample_bilinear_scaled(flows[2 + s], (img_h // 2 ** s, img_w // 2 ** s), 4.0) for s in range(4)]

@@ -521,6 +521,36 @@ def bias_leaky_relu_(y: torch.Tensor, bias: torch.Tensor, negative_slope: float 
     return _BiasLeakyReLU.apply(y, bias.contiguous(), negative_slope, bool(fork))
 
 
+class _UpsampleScaled(torch.autograd.Function):
+    """scale * F.interpolate(x, size, mode='bilinear') (align_corners=False) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, scale):
+        xc = x.contiguous()
+        B, C, h, w = xc.shape
+        out = torch.empty((B, C, H, W), device=xc.device, dtype=torch.float32)
+        with torch.cuda.device_of(xc):
+            _lib.call('uof_upsample_bilinear_fwd', _p(xc), _p(out), B * C, h, w, H, W, float(scale), _stream(xc))
+        ctx.dims = (B, C, h, w, H, W, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, h, w, H, W, scale = ctx.dims
+        g = g.contiguous()
+        gin = torch.empty((B, C, h, w), device=g.device, dtype=torch.float32)
+        with torch.cuda.device_of(g):
+            _lib.call('uof_upsample_bilinear_bwd', _p(g), _p(gin), B * C, h, w, H, W, scale, _stream(g))
+        return gin, None, None, None
+
+
+def upsample_bilinear_scaled(x: torch.Tensor, size, scale: float = 1.0) -> torch.Tensor:
+    """== F.interpolate(x, size, mode='bilinear') * scale (pwc_tf.py:119 ... 177; `size` = (H, W) >= x's), fused."""
+    _require_cuda(x)
+    H, W = int(size[0]), int(size[1])
+    return _UpsampleScaled.apply(x, H, W, float(scale))
+
+
 # ------------------------------------------------------------------------------------------ a9
 def _pyramid_launch(base, nimg, stride_img, B, C, H, W, sb, sc, sh, num_pyramid):
     lv = [torch.empty((nimg, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=base.device) for s in range(1, num_pyramid)]
