@@ -159,6 +159,12 @@ def algorithmic_bytes(name, args):
     if name == 'uof_bias_lrelu_bwd':            # read gout and y, write gx
         B, C, H, W = args[4:8]
         return 12 * B * C * H * W
+    if name in ('uof_upsample_bilinear_fwd', 'uof_upsample_bilinear_bwd'):      # read one side, write the other
+        planes, h, w, H, W = (int(v) for v in args[2:7])
+        return 4 * planes * (h * w + H * W)
+    if name == 'uof_img_pyramid_stacked':      # read the triplet once, write level 0 and the coarser levels
+        nimg, B, C, H, W = (int(v) for v in args[9:14])
+        return int(4 * nimg * B * C * H * W * (2 + 0.25 + 0.0625))
     if name == 'uof_img_pyramid':
         nimg, B, C, H, W = args[7:12]
         return int(nimg * B * C * H * W * 4 * (1 + 1 / 4 + 1 / 16))
@@ -180,6 +186,8 @@ class KernelObserver:
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))
             if name == 'uof_warp_bwd':
                 key += '+gx' if args[3].value else ''
+        elif name.startswith('uof_upsample_bilinear'):
+            key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in args[2:7]))
         elif name == 'uof_bias_lrelu_bwd2':      # same key as the one-gradient form, '+g2' when two gradients are summed
             key = 'uof_bias_lrelu_bwd[%s]%s' % ('x'.join(str(int(d)) for d in args[7:11]), '+g2' if args[2] else '')
         elif name.startswith('uof_bias_lrelu'):

@@ -57,17 +57,38 @@ upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
   const int x_lo = max((int)floorf(((float)j - 0.5f) * inv_rx - 0.5f) - 1, 0), x_hi = min((int)ceilf(((float)j + 1.5f) * inv_rx - 0.5f) + 1, W - 1);
   const float* g = gout + plane * ((long long)H * W);
   float acc = 0.0f;
-  for (int y = y_lo; y <= y_hi; ++y) {
-    const Tap ty = tap_of(y, ry, h);
-    const float wy = (ty.i0 == i ? ty.l0 : 0.0f) + (ty.i1 == i ? ty.l1 : 0.0f);
-    if (wy == 0.0f) continue;
-    float row = 0.0f;
-    for (int x = x_lo; x <= x_hi; ++x) {
-      const Tap tx = tap_of(x, rx, w);
-      const float wx = (tx.i0 == j ? tx.l0 : 0.0f) + (tx.i1 == j ? tx.l1 : 0.0f);
-      row = fmaf(wx, __ldg(g + (long long)y * W + x), row);
+  constexpr int kMaxTaps = 16;                 // candidate columns whose weights are kept in registers (x4: 14)
+  if (x_hi - x_lo < kMaxTaps) {
+    float wx[kMaxTaps];
+#pragma unroll
+    for (int k = 0; k < kMaxTaps; ++k) {
+      const Tap tx = tap_of(min(x_lo + k, W - 1), rx, w);
+      wx[k] = (x_lo + k <= x_hi) ? (tx.i0 == j ? tx.l0 : 0.0f) + (tx.i1 == j ? tx.l1 : 0.0f) : 0.0f;
     }
-    acc = fmaf(wy, row, acc);
+    for (int y = y_lo; y <= y_hi; ++y) {
+      const Tap ty = tap_of(y, ry, h);
+      const float wy = (ty.i0 == i ? ty.l0 : 0.0f) + (ty.i1 == i ? ty.l1 : 0.0f);
+      if (wy == 0.0f) continue;
+      const float* gr = g + (long long)y * W + x_lo;
+      float row = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kMaxTaps; ++k)
+        if (wx[k] != 0.0f) row = fmaf(wx[k], __ldg(gr + k), row);
+      acc = fmaf(wy, row, acc);
+    }
+  } else {
+    for (int y = y_lo; y <= y_hi; ++y) {
+      const Tap ty = tap_of(y, ry, h);
+      const float wy = (ty.i0 == i ? ty.l0 : 0.0f) + (ty.i1 == i ? ty.l1 : 0.0f);
+      if (wy == 0.0f) continue;
+      float row = 0.0f;
+      for (int x = x_lo; x <= x_hi; ++x) {
+        const Tap tx = tap_of(x, rx, w);
+        const float wx = (tx.i0 == j ? tx.l0 : 0.0f) + (tx.i1 == j ? tx.l1 : 0.0f);
+        row = fmaf(wx, __ldg(g + (long long)y * W + x), row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
   }
   gin[t] = scale * acc;
 }
