@@ -285,6 +285,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default; stdout carries the ONE JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     import unopticalflow_b200 as u
