@@ -157,6 +157,25 @@ def cases(B=8, H=256, W=832):
     yield ('img_pyramid[levels 1..2 of the 3 images, one launch]', int(3 * B * 3 * H * W * 4 * (1 + 1 / 4 + 1 / 16)),
            [lambda t=t, pp=pp: _lib.call('uof_img_pyramid', ops._p(t), H * t.stride(2), t.stride(0), t.stride(1), t.stride(2), pp, S,
                                          3, B, 3, H, W, ops._stream(anchor)) for t, pp in zip(trip, pptr)])
+    # stacked triplet pyramid with the dense level-0 copy (what Model_flow.forward calls)
+    lv0 = [torch.empty(3, B, 3, H, W, device=dev) for _ in range(k)]
+    slots = (ctypes.c_int * 3)(0, 2, 1)
+    keep.append((lv0, slots))
+    yield ('img_pyramid_stacked[3 images, levels 0..2, one launch]', int(3 * B * 3 * H * W * 4 * (2 + 1 / 4 + 1 / 16)),
+           [lambda t=t, pp=pp, o0=o0: _lib.call('uof_img_pyramid_stacked', ops._p(t), H * t.stride(2), t.stride(0), t.stride(1),
+                                                t.stride(2), ops._p(o0), slots, pp, S, 3, B, 3, H, W, ops._stream(anchor))
+            for t, pp, o0 in zip(trip, pptr, lv0)])
+    # fused x4 bilinear up-sampling + scale of the finest flow (2B x 2 x H/4 x W/4 -> H x W)
+    fins = [r(B2, 2, H // 4, W // 4) for _ in range(k)]
+    fouts = [torch.empty(B2, 2, H, W, device=dev) for _ in range(k)]
+    keep.append((fins, fouts))
+    nup = 4 * B2 * 2 * (H * W + (H // 4) * (W // 4))
+    yield ('upsample_x4_fwd[%dx2x%dx%d]' % (B2, H // 4, W // 4), nup,
+           [lambda a=a, o=o: _lib.call('uof_upsample_bilinear_fwd', ops._p(a), ops._p(o), B2 * 2, H // 4, W // 4, H, W, 4.0,
+                                       ops._stream(anchor)) for a, o in zip(fins, fouts)])
+    yield ('upsample_x4_bwd[%dx2x%dx%d]' % (B2, H // 4, W // 4), nup,
+           [lambda a=a, o=o: _lib.call('uof_upsample_bilinear_bwd', ops._p(o), ops._p(a), B2 * 2, H // 4, W // 4, H, W, 4.0,
+                                       ops._stream(anchor)) for a, o in zip(fins, fouts)])
     # fused bias + LeakyReLU of the largest decoder activation (2B x 128 x H/4 x W/4)
     ah, aw = H // 4, W // 4
     ka = 3
