@@ -44,39 +44,40 @@ __device__ __forceinline__ SplatGeom splat_geom(float fx, float fy, int b, int y
 }
 
 // ---------------------------------------------------------------------------- range map (C == 1)
-// u == nullptr means "splat ones".
-__global__ void __launch_bounds__(256)
-splat1_fwd_kernel(const float* __restrict__ u, const float2* __restrict__ flow, float* __restrict__ out, int B, int H, int W) {
-  const long long n = (long long)B * H * W;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < n;
+// u == nullptr means "splat ones".  grid = (x chunks, H, B): no index decoding, and everything inside the image is
+// 32-bit (offsets y*W + x relative to the image base; the first version carried 64-bit flat targets through the
+// shuffles and decoded a 64-bit linear thread index with two div/mod pairs).
+__global__ void __launch_bounds__(128)
+splat1_fwd_kernel(const float* __restrict__ u, const float2* __restrict__ flow, float* __restrict__ out, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const size_t base = (size_t)blockIdx.z * H * W;
+  const bool live = x < W;
   const int lane = threadIdx.x & 31;
-  SplatGeom g;
-  float v = 0.0f;
+  int ia = -1, ib = -1, ic = -1, id = -1;                    // offsets inside the image, -1 = out of bounds
+  float ca = 0.0f, cb = 0.0f, cc = 0.0f, cd = 0.0f;
   if (live) {
-    const int x = (int)(t % W), y = (int)((t / W) % H), b = (int)(t / ((long long)W * H));
+    const size_t t = base + (size_t)y * W + x;
     const float2 f = __ldg(flow + t);
-    g = splat_geom(f.x, f.y, b, y, x, H, W);
-    v = u ? __ldg(u + t) : 1.0f;
-  } else {
-    g.ia = g.ib = g.ic = g.id = -1;
-    g.wa = g.wb = g.wc = g.wd = 0.0f;
+    const SplatGeom g = splat_geom(f.x, f.y, 0, y, x, H, W);   // b = 0: targets relative to the image
+    const float v = u ? __ldg(u + t) : 1.0f;
+    ia = (int)g.ia; ib = (int)g.ib; ic = (int)g.ic; id = (int)g.id;
+    ca = v * g.wa; cb = v * g.wb; cc = v * g.wc; cd = v * g.wd;
   }
-  float ca = v * g.wa, cb = v * g.wb, cc = v * g.wc, cd = v * g.wd;
   // warp aggregation: hand my right-hand column (x1) to lane+1 if it is that lane's left-hand column
-  const long long nic = __shfl_up_sync(kFullMask, g.ic, 1), nid = __shfl_up_sync(kFullMask, g.id, 1);
+  const int nic = __shfl_up_sync(kFullMask, ic, 1), nid = __shfl_up_sync(kFullMask, id, 1);
   const float ncc = __shfl_up_sync(kFullMask, cc, 1), ncd = __shfl_up_sync(kFullMask, cd, 1);
-  const bool take = lane > 0 && nic == g.ia && nid == g.ib && (g.ia >= 0 || g.ib >= 0);
+  const bool take = lane > 0 && nic == ia && nid == ib && (ia >= 0 || ib >= 0);
   const bool taken = __shfl_down_sync(kFullMask, (int)take, 1) && lane < 31;
   if (take) {
     ca += ncc;
     cb += ncd;
   }
-  if (g.ia >= 0) atomicAdd(out + g.ia, ca);
-  if (g.ib >= 0) atomicAdd(out + g.ib, cb);
+  float* o = out + base;
+  if (ia >= 0) atomicAdd(o + ia, ca);
+  if (ib >= 0) atomicAdd(o + ib, cb);
   if (!taken) {
-    if (g.ic >= 0) atomicAdd(out + g.ic, cc);
-    if (g.id >= 0) atomicAdd(out + g.id, cd);
+    if (ic >= 0) atomicAdd(o + ic, cc);
+    if (id >= 0) atomicAdd(o + id, cd);
   }
 }
 
@@ -208,7 +209,8 @@ extern "C" int uof_splat_fwd(const float* u, const float* flow, float* out, int 
   UOF_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * C * sizeof(float), stream));
   const float2* f2 = reinterpret_cast<const float2*>(flow);
   if (C == 1) {
-    splat1_fwd_kernel<<<(unsigned)ceil_div_ll(npix, 256), 256, 0, stream>>>(u, f2, out, B, H, W);
+    UOF_REQUIRE(H <= 65535 && B <= 65535 && (long long)H * W < (1ll << 31), "splat_fwd: image too large for one launch");
+    splat1_fwd_kernel<<<dim3(ceil_div(W, 128), H, B), 128, 0, stream>>>(u, f2, out, H, W);
   } else if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(u) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     splat_fwd_kernel<true><<<(unsigned)ceil_div_ll(npix * (C / 4), 256), 256, 0, stream>>>(u, f2, out, B, H, W, C);
   } else {

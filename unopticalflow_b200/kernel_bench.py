@@ -190,7 +190,10 @@ def cases(B=8, H=256, W=832):
     yield ('bias_lrelu_bwd[%dx128x%dx%d]' % (B2, ah, aw), 12 * nact,
            [lambda a=a, g=g, o=o: _lib.call('uof_bias_lrelu_bwd', ops._p(g), ops._p(a), ops._p(o), ops._p(gbias), B2, 128, ah, aw, 0.1,
                                             ops._stream(anchor)) for a, g, o in zip(acts, gacts, gxs)])
-    fl_nhwc = [r(B2, H, W, 2) * 2 for _ in range(k)]
+    # full-resolution flows as the decoder produces them (x4 bilinear up-sampling of a coarse field, sigma ~2.5 px), NHWC;
+    # per-pixel random flows (no coinciding corners between neighbours, nothing to aggregate) cost 47 us instead
+    fl_nhwc = [torch.nn.functional.interpolate(r(B2, 2, H // 4, W // 4) * 2.5, size=(H, W), mode='bilinear', align_corners=False)
+               .permute(0, 2, 3, 1).contiguous() for _ in range(k)]
     rm = [torch.empty(B2, H, W, 1, device=dev) for _ in range(k)]
     keep.append((fl_nhwc, rm))
     yield ('range_map (splat ones) [%dx%dx%d]' % (B2, H, W), 16 * B2 * H * W,
