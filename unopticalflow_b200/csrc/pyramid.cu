@@ -43,16 +43,15 @@ __global__ void __launch_bounds__(256) pyramid_generic_kernel(const __grid_const
   P.out[l][e] = s / (float)((ye - ys) * (xe - xs));
 }
 
-// thread = one 4x4 input block of one (image, batch, channel) plane
-__global__ void __launch_bounds__(256) pyramid_pow2_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
+// thread = one 4x4 input block of one (image, batch, channel) plane; block = 32 x 4 such blocks, grid = (W/128, H/16,
+// planes): only the plane index is decoded (block-uniform), the first version decoded a 64-bit linear thread index
+__global__ void __launch_bounds__(128) pyramid_pow2_kernel(const __grid_constant__ PyrParams P, const float* __restrict__ img) {
   const int W4 = P.W >> 2, H4 = P.H >> 2;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)P.nimg * P.B * P.C * H4 * W4;
-  if (t >= total) return;
-  const int bx = (int)(t % W4), by = (int)((t / W4) % H4);
-  long long plane_id = t / ((long long)W4 * H4);                // (im*B + b)*C + c
-  const int c = (int)(plane_id % P.C);
-  const int b = (int)((plane_id / P.C) % P.B), im = (int)(plane_id / ((long long)P.C * P.B));
+  const int bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (bx >= W4 || by >= H4) return;
+  long long plane_id = blockIdx.z;                              // (im*B + b)*C + c
+  const int c = (int)(blockIdx.z % (unsigned)P.C);
+  const int b = (int)((blockIdx.z / (unsigned)P.C) % (unsigned)P.B), im = (int)(blockIdx.z / (unsigned)(P.C * P.B));
   const float* src = img + im * P.si + b * P.sb + c * P.sc + (long long)(4 * by) * P.sh + 4 * bx;
   float4 r[4];
 #pragma unroll
@@ -115,8 +114,8 @@ extern "C" int uof_img_pyramid_stacked(const float* img, long long stride_img, l
   const bool fast = H % 4 == 0 && W % 4 == 0 && P.nout <= 2 && strides_ok && (!out0 || (reinterpret_cast<uintptr_t>(out0) & 15u) == 0);
   UOF_REQUIRE(fast || (!out0 && !slot), "img_pyramid: the stacked level-0 copy / slot order need H, W %% 4 == 0, <= 3 levels and 16-byte aligned strides");
   if (fast) {
-    const long long threads = (long long)nimg * B * C * (H / 4) * (W / 4);
-    pyramid_pow2_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, stream>>>(P, img);
+    UOF_REQUIRE((long long)nimg * B * C <= 65535 && H / 16 + 1 <= 65535, "img_pyramid: too many planes for one launch");
+    pyramid_pow2_kernel<<<dim3(ceil_div(W / 4, 32), ceil_div(H / 4, 4), nimg * B * C), 128, 0, stream>>>(P, img);
   } else {
     pyramid_generic_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(P, img);
   }
