@@ -30,7 +30,8 @@ def gpu(t, grad=False):
 LEVEL_SHAPES = [(2, 196, 4, 13), (2, 128, 8, 26), (2, 96, 16, 52), (2, 64, 32, 104), (2, 32, 64, 208)]
 
 
-@pytest.mark.parametrize('shape', [(2, 8, 6, 9), (1, 5, 11, 7), (1, 3, 1, 1), (3, 17, 33, 70)] + LEVEL_SHAPES)
+# (6, 96, 16, 52): 24 tiles -> split-K of 5 over 12 channel slabs, i.e. a cluster of 5 CTAs whose last one has no channels
+@pytest.mark.parametrize('shape', [(2, 8, 6, 9), (1, 5, 11, 7), (1, 3, 1, 1), (3, 17, 33, 70), (6, 96, 16, 52)] + LEVEL_SHAPES)
 def test_cost_volume_vs_oracle(U, shape):
     g = torch.Generator().manual_seed(sum(shape))
     B, C, H, W = shape

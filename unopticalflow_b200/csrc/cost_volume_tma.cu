@@ -11,6 +11,7 @@
 //     the 148 SMs (e.g. W = 208: 16x16 tiles divide the row exactly, 2.8 waves instead of 3.03 -> 4).
 // Thread/register layout is the one described in cost_volume.cu: 192 threads = 64 pixel quads x 3 dy-groups,
 // 108 accumulators (forward) or 108 coefficients (backward) per thread, 12-float sliding register window.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "cost_volume.h"
@@ -51,15 +52,21 @@ __device__ __forceinline__ float* align128(unsigned char* p) {
 }
 
 // ------------------------------------------------------------------------------------------- forward
-template <class T>
+// CLUSTER: the `ksplit` CTAs that share a tile (split over channels) form a thread-block cluster (1,1,ksplit); their
+// partial accumulators are combined through distributed shared memory by the cluster's rank-0 CTA, which alone writes the
+// tile -- no fp32 atomics into a zero-filled output (the non-cluster split-K path, kept for ksplit > 8).
+constexpr int kStashFloats = DYG * ND * PX * NT;          // one CTA's accumulators: 108 x 192 floats = 81 KB
+
+template <class T, bool CLUSTER>
 __global__ void __launch_bounds__(NT, 2)
 cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                            float* __restrict__ out, int C, int H, int W, long long out_bs, int ksplit, float inv_c) {
   constexpr int TH = T::TH, TW = T::TW, HTH = T::HTH, HTW = T::HTW, S1 = T::S1, S2 = T::S2;
   constexpr int kStage = S1 + S2;
+  constexpr int kBarOff = (CLUSTER && kStashFloats > NSTAGE_F * kStage) ? kStashFloats : NSTAGE_F * kStage;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* smem = align128(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE_F * kStage);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* empty = full + NSTAGE_F;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -69,8 +76,8 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
   const int nchunks = (C + CK - 1) / CK;
   const int per = (nchunks + ksplit - 1) / ksplit;
   const int k_begin = ks * per, k_end = min(nchunks, k_begin + per);
-  if (k_begin >= k_end) return;
-  const int n = k_end - k_begin;
+  if (!CLUSTER && k_begin >= k_end) return;
+  const int n = max(k_end - k_begin, 0);              // cluster: a CTA without channels still joins the reduction (zeros)
 
   if (tid == 0) {
 #pragma unroll
@@ -134,6 +141,45 @@ cost_volume_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
   }
 
   const int y = y0 + ty, x = x0 + PX * gx;
+  if (CLUSTER) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();          // == ks: the cluster spans the split
+    float* stash = smem;                                 // [accumulator][thread]; the stage buffers are free now
+    __syncthreads();
+    if (rank != 0) {
+#pragma unroll
+      for (int r = 0; r < DYG; ++r)
+#pragma unroll
+        for (int jd = 0; jd < ND; ++jd)
+#pragma unroll
+          for (int p = 0; p < PX; ++p) stash[((r * ND + jd) * PX + p) * NT + tid] = acc[r][jd][p];
+    }
+    cluster.sync();
+    if (rank == 0) {
+      for (unsigned rr = 1; rr < (unsigned)ksplit; ++rr) {
+        const float* remote = cluster.map_shared_rank(stash, rr);
+#pragma unroll
+        for (int r = 0; r < DYG; ++r)
+#pragma unroll
+          for (int jd = 0; jd < ND; ++jd)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[r][jd][p] += remote[((r * ND + jd) * PX + p) * NT + tid];
+      }
+      if (y < H && x < W) {
+        float* ob = out + (size_t)b * out_bs + (size_t)y * W + x;
+        const size_t plane = (size_t)H * W;
+#pragma unroll
+        for (int r = 0; r < DYG; ++r)
+#pragma unroll
+          for (int jd = 0; jd < ND; ++jd)
+            *reinterpret_cast<float4*>(ob + (size_t)((dg * DYG + r) * ND + jd) * plane) =
+                make_float4(acc[r][jd][0] * inv_c, acc[r][jd][1] * inv_c, acc[r][jd][2] * inv_c, acc[r][jd][3] * inv_c);
+      }
+    }
+    cluster.sync();                                      // the other CTAs' shared memory stays alive until rank 0 has read it
+    return;
+  }
   if (y >= H || x >= W) return;
   float* ob = out + (size_t)b * out_bs + (size_t)y * W + x;
   const size_t plane = (size_t)H * W;
@@ -398,6 +444,11 @@ constexpr size_t fwd_smem() {
   return NSTAGE_F * (T::S1 + T::S2) * sizeof(float) + 2 * NSTAGE_F * sizeof(uint64_t) + 128;
 }
 template <class T>
+constexpr size_t fwd_cluster_smem() {
+  constexpr size_t stage = NSTAGE_F * (T::S1 + T::S2), stash = kStashFloats;
+  return (stage > stash ? stage : stash) * sizeof(float) + 2 * NSTAGE_F * sizeof(uint64_t) + 128;
+}
+template <class T>
 constexpr size_t bwd_smem() {
   return (NSTAGE * T::S2 + 2 * T::kRed) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 128;
 }
@@ -441,6 +492,27 @@ int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H
     if (force) ksplit = max(1, min(atoi(force), ceil_div(C, CK)));
   }
   UOF_REQUIRE((long long)B * ksplit <= 65535 && ty <= 65535, "cost_volume_fwd: grid too large");
+  static const bool no_cluster = getenv("UOF_CV_NO_CLUSTER") != nullptr;
+  if (ksplit >= 2 && ksplit <= 8 && !no_cluster) {     // split-K combined through distributed shared memory: no atomics, no zero-fill
+    auto ck = cost_volume_fwd_tma_kernel<T, true>;
+    UOF_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_cluster_smem<T>()));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tx, ty, B * ksplit);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = fwd_cluster_smem<T>();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)ksplit;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float inv_c = 1.0f / (float)C;
+    UOF_CUDA(cudaLaunchKernelEx(&cfg, ck, m1, m2, out, C, H, W, out_bs, ksplit, inv_c));
+    count_launch();
+    return check_launch("cost_volume_fwd (tma, cluster split-K)");
+  }
   if (ksplit > 1)
     UOF_CUDA(cudaMemset2DAsync(out, out_bs * sizeof(float), 0, (size_t)UOF_NUM_DISPLACEMENTS * H * W * sizeof(float), B, stream));
   const long long tiles = (long long)tx * ty * B;
@@ -452,7 +524,7 @@ int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H
     count_launch();
     return check_launch("cost_volume_fwd (tma, persistent)");
   }
-  auto kern = cost_volume_fwd_tma_kernel<T>;
+  auto kern = cost_volume_fwd_tma_kernel<T, false>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<T>()));
   kern<<<dim3(tx, ty, B * ksplit), NT, fwd_smem<T>(), stream>>>(m1, m2, out, C, H, W, out_bs, ksplit, 1.0f / (float)C);
   count_launch();
