@@ -285,9 +285,19 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default; stdout carries the ONE JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/WARN/INFO) on stdout when the communicator is created, and
+        # stdout carries the ONE JSON line: create the communicator with file descriptor 1 pointed at stderr.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     import unopticalflow_b200 as u
     from unopticalflow_b200 import _lib, train as T
