@@ -535,7 +535,7 @@ __device__ __forceinline__ void consis_load(const float* __restrict__ base, int 
   }
 }
 
-constexpr int kConsisFwdWarps = 8;   // forward: 8 warps share one RED pair (block_accumulate)
+constexpr int kConsisFwdWarps = 4;   // forward: the warps of a block share one RED pair (block_accumulate)
 
 template <int VEC>
 __global__ void __launch_bounds__(kConsisFwdWarps * 32)
