@@ -285,7 +285,7 @@ __device__ __forceinline__ float edge_l1(const float* a, const float* b) {
   return fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2]);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 smooth_fwd_quad_kernel(const __grid_constant__ SmoothParams P, float* __restrict__ sums, float* __restrict__ loss) {
   __shared__ float4 ring_s[kWarpsPerBlock][kQDepth * kRowVals * 32];
   const int lane = threadIdx.x & 31;
