@@ -45,6 +45,19 @@ def test_argument_validation_without_gpu(lib):
         _lib.call('uof_warp_fwd', ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 3, 4, 4, 0, 0, 1, None)
     with pytest.raises(ValueError, match='nlevels'):
         _lib.call('uof_photo_loss_fwd', None, 0, 1, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), None)
+    P = ctypes.c_void_p(16)
+    with pytest.raises(ValueError, match='up-sampling only'):
+        _lib.call('uof_upsample_bilinear_fwd', P, P, 2, 8, 8, 4, 16, 1.0, None)
+    with pytest.raises(ValueError, match='null pointer'):
+        _lib.call('uof_upsample_bilinear_bwd', None, P, 2, 4, 4, 8, 8, 1.0, None)
+    with pytest.raises(ValueError, match='batch stride'):
+        _lib.call('uof_bias_lrelu_bwd2', P, 10, None, 0, P, P, P, 2, 4, 8, 8, 0.1, None)
+    with pytest.raises(ValueError, match='bad slot'):
+        slots = (ctypes.c_int * 3)(0, 5, 1)
+        outs = (ctypes.c_void_p * 2)(16, 16)
+        _lib.call('uof_img_pyramid_stacked', P, 64, 192, 64, 8, P, slots, outs, 3, 3, 1, 3, 8, 8, None)
+    with pytest.raises(ValueError, match='too large for one launch'):
+        _lib.call('uof_splat_fwd', None, P, P, 1, 70000, 4, 1, None)
 
 
 def test_library_missing_fails_loudly(tmp_path, monkeypatch):

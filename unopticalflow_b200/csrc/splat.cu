@@ -206,10 +206,10 @@ extern "C" int uof_splat_fwd(const float* u, const float* flow, float* out, int 
   UOF_REQUIRE(u || C == 1, "splat_fwd: u == NULL (ones) needs C == 1");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long npix = (long long)B * H * W;
+  UOF_REQUIRE(C != 1 || (H <= 65535 && B <= 65535 && (long long)H * W < (1ll << 31)), "splat_fwd: image too large for one launch");
   UOF_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * C * sizeof(float), stream));
   const float2* f2 = reinterpret_cast<const float2*>(flow);
   if (C == 1) {
-    UOF_REQUIRE(H <= 65535 && B <= 65535 && (long long)H * W < (1ll << 31), "splat_fwd: image too large for one launch");
     splat1_fwd_kernel<<<dim3(ceil_div(W, 128), H, B), 128, 0, stream>>>(u, f2, out, H, W);
   } else if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(u) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     splat_fwd_kernel<true><<<(unsigned)ceil_div_ll(npix * (C / 4), 256), 256, 0, stream>>>(u, f2, out, B, H, W, C);
