@@ -456,10 +456,13 @@ extern "C" int uof_warp_bwd(const float* gout, const float* x, const float* flow
   UOF_REQUIRE(gflow, "warp_bwd: gflow is null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float sx = coord_scale(W, align_corners), sy = coord_scale(H, align_corners);
+  if (!channels_last) {      // argument validation before the first CUDA call
+    const int nchunk = ceil_div(C, pick_cch()), runs = ceil_div(W, 32 * pick_pxt(W, true));
+    UOF_REQUIRE(B <= 65535 && nchunk <= 65535 && (long long)H * runs * runs < (1ll << 31), "warp_bwd: grid too large (B=%d)", B);
+  }
   if (gx) UOF_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * C * H * W * sizeof(float), stream));
   if (!channels_last) {
     const int nchunk = ceil_div(C, pick_cch()), pxt = pick_pxt(W, true), runs = ceil_div(W, 32 * pxt);
-    UOF_REQUIRE(B <= 65535 && nchunk <= 65535 && (long long)H * runs * runs < (1ll << 31), "warp_bwd: grid too large (B=%d)", B);
     if (nchunk > 1) UOF_CUDA(cudaMemsetAsync(gflow, 0, (size_t)B * 2 * H * W * sizeof(float), stream));
     if (pxt == 4)
       launch_bwd_nchw<4>(gout, x, flow, gx, gflow, B, C, H, W, nchunk, runs, use_mask, align_corners, sx, sy, stream);
