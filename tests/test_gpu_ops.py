@@ -652,3 +652,21 @@ def test_diff_weight_and_masked_mean_seams_with_gradients(U):
     assert_close(g3, r3, REL_TOL)
     for a, b in zip(torch.autograd.grad(g3.sum(), c3), torch.autograd.grad(r3.sum(), d3)):
         assert_close(a, b, REL_TOL)
+
+
+def test_fallback_kernel_variants_pass_the_same_parity_tests():
+    """Every fast kernel variant has a fallback selected by shape or by an environment switch (README): re-run the operator
+    parity tests in a fresh process with ALL fast variants switched off (cp.async cost volume without persistence, cluster
+    split-K and the small-level kernel; one-pixel smoothness; fused-direction photometric forward, split backward)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, UOF_DISABLE_TMA='1', UOF_CV_NO_PERSIST='1', UOF_CV_NO_CLUSTER='1', UOF_CV_NO_SMALL='1',
+               UOF_SMOOTH_NO_QUAD='1', UOF_PHOTO_FWD_NO_PAIR='1', UOF_PHOTO_NO_PAIR='1')
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = ('test_cost_volume_vs_oracle or test_corr_concat_matches_cat or test_photometric_fused_vs_oracle or '
+           'test_smooth_and_consis_vs_oracle or test_smooth_wide_piecewise_linear_flows or test_losses_golden_from_reference')
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_gpu_ops.py'), '-q', '-m', 'gpu', '-k', sel,
+                          '-p', 'no:cacheprovider'], capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(here))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert ' passed' in out.stdout and 'failed' not in out.stdout
