@@ -46,7 +46,11 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='triplets per GPU (kitti.yaml / train.py:168 default 8)')
+    ap.add_argument('--global-batch', type=int, default=0,
+                    help='strong scaling (BASELINE.json configs[4]): total triplets per step, split evenly over the ranks '
+                         '(overrides --batch; 64 -> 64/32/16/8 per rank at N=1/2/4/8)')
     ap.add_argument('--hw', type=int, nargs=2, default=[256, 832])
+    ap.add_argument('--no-gpu-baseline', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='do not capture the step in a CUDA graph')
@@ -227,24 +231,101 @@ class KernelObserver:
         return out
 
 
-# ------------------------------------------------------------------------------ CPU reference
-def cpu_reference_steps(steps, warmup, H, W, sample_batch=1):
-    """The reference's CPU path (oracle port of Model_flow + train.py:137-152) on this host's cores."""
+# ------------------------------------------------------------------------------ reference arms
+NBUF = 4          # distinct input batches rotated through every timed loop
+
+
+def workload_config(B, world, H, W, scaling):
+    """`config` of the JSON line: the workload only, identical for the b200 and the reference arm of one launch."""
+    return {'workload': 'BASELINE.json configs[1]: kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam, train.py:137-152), '
+                        'synthetic %dx%d triplets, batch %d per GPU, fp32 (TF32 off)' % (H, W, B),
+            'img_hw': [H, W], 'batch_per_gpu': B, 'global_batch': B * world, 'frame_pairs_per_triplet': 2,
+            'parallelism': 'dp%d (one process per GPU, batch sharded by sample, %s scaling)' % (world, scaling) if world > 1 else 'single',
+            'tf32': False,
+            'l2': '%d distinct input batches (%.0f MB each, %.0f MB total vs 126 MB L2) rotated; the activations a step writes '
+                  'and re-reads (GBs) flush L2 between iterations' % (NBUF, B * 9 * H * W * 4 / 1e6, NBUF * B * 9 * H * W * 4 / 1e6)}
+
+
+def reference_model(device):
+    """(model, kind, step): the reference's Model_flow + train.py:35-39,137-152 restated around it (train.py itself does not
+    import in this image).  kind 'reference' = the UNMODIFIED reference installed in baseline/_ref by
+    baseline/install_ref.py (its own core.networks.get_model / core.config.generate_loss_weights_dict, stock ATen code
+    path, none of this repo's kernels); kind 'port' = the oracle restatement, only when baseline/_ref is absent."""
     import torch
-    from oracle import model as omodel
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from unopticalflow_b200 import train as T
+    cfg = T.KITTI_CFG
+    try:
+        from baseline import install_ref
+        have_ref = install_ref.available()
+    except Exception:
+        have_ref = False
     torch.manual_seed(0)
-    model = omodel.Model_flow(omodel.Cfg)
-    opt = omodel.make_optimizer(model)
+    if have_ref:
+        net = install_ref.load()
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                    # the reference prints a banner from Model_flow.__init__; stdout carries ONE JSON line
+        try:
+            model = net.get_model(cfg.mode)(cfg)
+            sys.stdout.flush()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        import core.config as ref_config                      # the reference's own loss-weight dict (config_utils.py:3-9)
+        weights = ref_config.generate_loss_weights_dict(cfg)
+        kind = 'reference'
+    else:
+        from oracle import model as omodel
+        model = omodel.Model_flow(cfg)
+        weights = T.generate_loss_weights_dict(cfg)
+        kind = 'port'
+    model = model.to(device)
+    model.train()
+    optimizer = torch.optim.Adam([{'params': filter(lambda p: p.requires_grad, model.parameters()), 'lr': cfg.lr}])   # train.py:39
+
+    def step(inputs):                    # train.py:137-152
+        optimizer.zero_grad()
+        loss_pack = model(inputs)
+        loss_list = []
+        for key in list(loss_pack.keys()):
+            loss_list.append((weights[key] * loss_pack[key].mean()).unsqueeze(0))
+        loss = torch.cat(loss_list, 0).sum()
+        loss.backward()
+        optimizer.step()
+        return loss.detach()
+    return model, kind, step
+
+
+def cpu_reference_steps(steps, warmup, H, W, batch, budget_s=240.0):
+    """The reference's own CPU implementation of the training step on this host's cores, all threads.  Each step is a batch
+    of `batch` triplets unless the projected run would exceed `budget_s`, in which case the sample shrinks (and says so)."""
+    import warnings
+    import torch
+    warnings.filterwarnings('ignore')
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    model, kind, step = reference_model(torch.device('cpu'))
     gen = torch.Generator().manual_seed(1234)
-    xs = [torch.rand(sample_batch, 3, 3 * H, W, generator=gen) for _ in range(2)]
-    for i in range(warmup):
-        omodel.train_step(model, opt, xs[i % 2])
+    sample = batch
+    t0 = time.perf_counter()
+    step(torch.rand(1, 3, 3 * H, W, generator=gen))              # probe (also the first warm-up): one triplet
+    t1 = time.perf_counter() - t0
+    while sample > 1 and 0.8 * t1 * sample * (steps + warmup) > budget_s:      # B=8 runs ~20 % faster per sample than B=1
+        sample //= 2
+    xs = [torch.rand(sample, 3, 3 * H, W, generator=gen) for _ in range(NBUF)]
+    for i in range(max(warmup - 1, 1)):
+        step(xs[i % NBUF])
     t0 = time.perf_counter()
     for i in range(steps):
-        omodel.train_step(model, opt, xs[i % 2])
+        step(xs[i % NBUF])
     dt = time.perf_counter() - t0
-    return dt / steps, torch.get_num_threads()
+    return dt / steps, torch.get_num_threads(), kind, sample
+
+
+def describe_sample(kind, sample, batch, cores, s_per_step):
+    what = ('the UNMODIFIED reference (baseline/_ref: core.networks.get_model(\'flow\') + train.py:137-152 restated)'
+            if kind == 'reference' else 'the CPU oracle port of the reference PyTorch path (baseline/_ref absent)')
+    return ('each step = %d triplet%s (%s batch of %d) through %s: zero_grad + fwd + bwd + Adam on %d torch threads, %.2f s/step'
+            % (sample, 's' if sample > 1 else '', 'the whole' if sample == batch else 'of the', batch, what, cores, s_per_step))
 
 
 def run_reference(args):
@@ -252,22 +333,56 @@ def run_reference(args):
     if rank != 0:
         return
     H, W = args.hw
-    sample = 1
-    s_per_step, cores = cpu_reference_steps(args.steps, args.warmup, H, W, sample)
+    B = per_rank_batch(args, max(args.gpus, 1))
+    s_per_step, cores, kind, sample = cpu_reference_steps(args.steps, args.warmup, H, W, B)
     value = 2.0 * sample / s_per_step
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': round(value, 4), 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(1e3 * s_per_step, 3),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam), synthetic 256x832 triplets',
-                   'img_hw': [H, W], 'batch_per_gpu': args.batch, 'frame_pairs_per_triplet': 2},
-        'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': 'each step = 1 triplet (of the batch of %d) through the CPU oracle port of the '
-                                   'reference PyTorch path: fwd+bwd+Adam, %d torch threads' % (args.batch, cores)},
+        'higher_is_better': True, 'scaling': scaling_of(args), 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(B, max(args.gpus, 1), H, W, scaling_of(args)),
+        'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': describe_sample(kind, sample, B, cores, s_per_step)},
         'e2e': {'value': round(value, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'note': 'one CPU process on rank 0 only (the reference has no multi-process CPU path); at N > 1 compare per-GPU numbers, '
+                'not this line, with the N-GPU aggregate',
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_baseline(torch, dev, B, H, W, host, steps=3, warmup=2):
+    """The number to beat: the reference's stock PyTorch/ATen/cuDNN path -- unmodified when baseline/_ref is
+    installed -- running the same training step on the SAME B200 inside this run: fp32, TF32 off, cudnn.benchmark on (the
+    reference leaves it off; on is the faster setting), eager like train.py, device-resident inputs, CUDA events."""
+    model, kind, step = reference_model(dev)
+    xs = [h.to(dev) for h in host[:2]]
+    for i in range(warmup):
+        step(xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, step, xs
+    torch.cuda.empty_cache()
+    return {'value': round(2 * B / (ms * 1e-3), 3), 'unit': UNIT, 'ms_per_step': round(ms, 3), 'kind': kind, 'steps': steps,
+            'warmup': warmup, 'what': ('%s Model_flow fwd+bwd+Adam (train.py:137-152), eager, batch %d of %dx%d triplets on this GPU, fp32 TF32 off'
+                                       % ('unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port of the reference', B, H, W))}
+
+
+def scaling_of(args):
+    return 'strong' if args.global_batch else 'weak'
+
+
+def per_rank_batch(args, world):
+    if args.global_batch:
+        assert args.global_batch % world == 0, '--global-batch must be a multiple of the number of ranks'
+        return args.global_batch // world
+    return args.batch
 
 
 # ----------------------------------------------------------------------------------- B200 arm
@@ -304,7 +419,7 @@ def run_b200(args):
     _lib.load()
     cfg = T.KITTI_CFG
     H, W = args.hw
-    B = args.batch
+    B = per_rank_batch(args, world)
     weights = T.generate_loss_weights_dict(cfg)
 
     torch.manual_seed(0)
@@ -317,7 +432,6 @@ def run_b200(args):
 
     # synthetic KITTI-shaped triplets; NBUF distinct resident batches (> L2 in total) are rotated so that no
     # timed iteration re-reads inputs left in L2 by the previous one (the step's activations are GBs anyway)
-    NBUF = 4
     gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
     host = [torch.rand(B, 3, 3 * H, W, generator=gen).pin_memory() for _ in range(NBUF)]
     resident = [h.to(dev) for h in host]
@@ -417,6 +531,11 @@ def run_b200(args):
         e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- the reference's own PyTorch path on this same GPU (rank 0 of a 1-GPU run) ------------------------
+    gpu_baseline = None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_baseline = gpu_reference_baseline(torch, dev, B, H, W, host)
+
     # ---- instrumented pass: CUDA events around every hand-written kernel launch ---------------------
     peak, peak_src = measured_peak_gbs()
     kernels = []
@@ -445,15 +564,12 @@ def run_b200(args):
         line = {
             'metric': METRIC, 'value': round(fp_per_step / (ms_step * 1e-3), 3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_step, 3),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'kitti.yaml flow-mode training step (Model_flow fwd+bwd+Adam), synthetic 256x832 triplets',
-                       'img_hw': [H, W], 'batch_per_gpu': B, 'global_batch': B * world, 'frame_pairs_per_triplet': 2,
-                       'triplets_per_s': round(B * world / (ms_step * 1e-3), 3),
-                       'parallelism': ('dp%d (one process per GPU, %s)' % (world, 'one flat NCCL all-reduce of the gradients inside the '
-                                       'CUDA graph' if use_graph else 'DistributedDataParallel, NCCL')) if world > 1 else 'single',
-                       'tf32': False, 'cuda_graph': bool(use_graph),
-                       'l2': '%d distinct resident input batches (%.0f MB total > 126 MB L2) rotated; step working set is GBs'
-                             % (NBUF, NBUF * in_bytes / 1e6)},
+            'higher_is_better': True, 'scaling': scaling_of(args), 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(B, world, H, W, scaling_of(args)),
+            'triplets_per_s': round(B * world / (ms_step * 1e-3), 3),
+            'execution': {'cuda_graph': bool(use_graph),
+                          'gradient_exchange': (('one flat NCCL all-reduce of the gradients inside the CUDA graph' if use_graph else
+                                                 'DistributedDataParallel, NCCL') if world > 1 else None)},
             'clocks': clocks,
             'e2e': {'value': round(fp_per_step / (ms_e2e * 1e-3), 3), 'unit': UNIT, 'ms_per_step': round(ms_e2e, 3),
                     'h2d_bytes_per_step': in_bytes * world, 'd2h_bytes_per_step': 4 * world,
@@ -502,11 +618,13 @@ def run_b200(args):
             line['kernels'] = kernels[:24]
         if isolated:
             line['kernels_isolated'] = isolated
+        if gpu_baseline:
+            line['gpu_baseline'] = gpu_baseline
+            line['gpu_baseline']['speedup'] = round(line['value'] / gpu_baseline['value'], 3)
         if world == 1 and not args.no_cpu_baseline:
-            s_per_step, cores = cpu_reference_steps(3, 1, H, W, 1)
-            line['cpu_baseline'] = {'value': round(2.0 / s_per_step, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': '3 timed steps (1 warm-up) of 1 triplet (of the batch of %d) through the CPU '
-                                              'oracle port: fwd+bwd+Adam, %.2f s/step' % (B, s_per_step)}
+            s_per_step, cores, kind, sample = cpu_reference_steps(3, 2, H, W, B, budget_s=30.0)
+            line['cpu_baseline'] = {'value': round(2.0 * sample / s_per_step, 4), 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                    'sample': '3 timed steps (2 warm-up); ' + describe_sample(kind, sample, B, cores, s_per_step)}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Teardown: a CUDA graph that holds captured NCCL kernels must be released before the communicator, and a

@@ -156,8 +156,8 @@ def main():
         arrs[name] = r_pack[k]
     npz('losses.npz', **arrs)
 
-    # ---- a10/a11 full training step, B=1 64x128 and B=2 64x64 ---------------------------
-    for tag, (B, H, W) in {'b1_64x128': (1, 64, 128), 'b2_64x64': (2, 64, 64)}.items():
+    # ---- a10/a11 full training step, B=1 64x128 and B=2 64x64, and BASELINE.json configs[0] (B=1 256x832) -----------
+    for tag, (B, H, W) in {'b1_64x128': (1, 64, 128), 'b2_64x64': (2, 64, 64), 'b1_256x832': (1, 256, 832)}.items():
         torch.manual_seed(0)
         ref_model = mfp.Model_flow(omodel.Cfg)
         torch.manual_seed(0)

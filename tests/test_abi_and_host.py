@@ -116,8 +116,9 @@ def test_product_never_imports_oracle():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the reference's CPU path = the oracle port) prints ONE JSON line with the contract's
-    keys; under a multi-rank launch every rank but 0 exits without work."""
+    """`bench.py --impl reference` (the reference's CPU path: the unmodified reference from baseline/_ref when installed,
+    else the oracle port) prints ONE JSON line with the contract's keys and the same `config` shape as the b200 arm;
+    under a multi-rank launch every rank but 0 exits without work."""
     import json
     import subprocess
     import sys
@@ -129,7 +130,9 @@ def test_bench_reference_arm_contract():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'frame-pairs/s' and d['higher_is_better'] is True and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    have_ref = os.path.exists(os.path.join(root, 'baseline', '_ref', 'MANIFEST.json'))
+    assert d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['config']['batch_per_gpu'] == 8 and d['config']['img_hw'] == [64, 128] and 'workload' in d['config']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     env = dict(os.environ, RANK='1', WORLD_SIZE='2')
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)

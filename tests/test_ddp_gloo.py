@@ -108,6 +108,11 @@ def test_install_rebinds_reference_seams():
     with pytest.raises(RuntimeError, match='no CPU fallback'):       # new instances route to the CUDA op
         PWC_tf().corr(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
     assert Model_flow.compute_loss_flow_smooth is not None
+    from unopticalflow_b200.install import uninstall
+    assert uninstall() == len(done)
+    assert mods['pwc_tf'].warp_flow is not ops.warp_flow and not hasattr(Model_flow, 'compute_loss_flow_smooth')
+    with pytest.raises(AssertionError, match='reference op chain'):
+        PWC_tf().corr(None, None)
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/core/networks'), reason='reference checkout not present')
@@ -121,3 +126,6 @@ def test_install_on_real_reference():
     for mod in ('net_utils', 'pwc_tf', 'model_flow_paper'):
         assert (mod, 'warp_flow') in done and sys.modules[mod].warp_flow is ops.warp_flow
     assert sys.modules['model_flow_paper'].SSIM is ops.SSIM
+    from unopticalflow_b200.install import uninstall
+    uninstall()
+    assert sys.modules['net_utils'].warp_flow is not ops.warp_flow

@@ -52,7 +52,12 @@ def test_step_matches_oracle_and_reference_golden(U, tag, B, H, W):
     gn = torch.stack([p.grad.norm() for p in m.parameters()]).cpu()
     assert_close(gn, g['grad_norms'], 2e-4, 'grad norms vs reference golden')
     err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x)
+    assert noise <= NOISE_CAP, 'run-to-run spread %.2e: a noisy kernel may not widen its own tolerance' % noise
     assert err <= REL_TOL + noise, (err, noise)
+
+
+# The run-to-run spread that may be added to the 1e-4 bar is itself capped.
+NOISE_CAP = 5e-5
 
 
 def global_grad_err_vs_same_gpu_oracle(m, ref, x, **loss_kw):
@@ -79,6 +84,51 @@ def global_grad_err_vs_same_gpu_oracle(m, ref, x, **loss_kw):
     n = float(rv.norm())
     noise = float((gv - gv2).norm()) / n + float((rv - rv2).norm()) / n
     return float((gv - rv).norm()) / n, noise
+
+
+def test_step_headline_config_b8_256x832(U):
+    """BASELINE.json configs[1] -- the shape bench.py times: B=8 triplets of 256x832.  Loss pack and the global parameter
+    gradient of the CUDA path against the oracle's op chain on the same GPU (same cuDNN convolutions, TF32 off; the CPU
+    oracle needs ~1 min for this batch), every sample of the batch.  This is the only place the TMA-persistent cost volume,
+    the +gx feature-warp backward and the 3B/2B batching are compared end to end at the benchmark shape."""
+    import copy
+    ref, m = build_pair(U)
+    x = torch.rand(8, 3, 3 * 256, 832, generator=torch.Generator().manual_seed(1234))
+    ref_gpu = copy.deepcopy(ref).cuda()
+    xc = x.cuda()
+    with torch.no_grad():
+        rp = ref_gpu(xc)
+    gp = m(xc)
+    for k in rp:
+        assert gp[k].shape == (8,)
+        assert_close(gp[k], rp[k], REL_TOL, k + ' vs same-GPU oracle chain, B=8 256x832')
+    del rp, gp, ref_gpu
+    err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x)
+    print('headline-config gradient: err vs same-GPU oracle %.2e, run-to-run spread %.2e' % (err, noise))
+    assert noise <= NOISE_CAP, noise
+    assert err <= REL_TOL + noise, (err, noise)
+
+
+def test_step_config0_b1_256x832_vs_cpu_oracle(U):
+    """BASELINE.json configs[0]: one 256x832 triplet, CUDA path against the CPU oracle (the reference's CPU-runnable case)
+    and against the step-level known answer recorded from the unmodified reference (SURVEY App. C recipe)."""
+    ref, m = build_pair(U)
+    x = torch.rand(1, 3, 3 * 256, 832, generator=torch.Generator().manual_seed(1234))
+    rp = ref(x)
+    O.total_loss(rp).backward()
+    gp = m(x.cuda())
+    O.total_loss(gp).backward()
+    for k in rp:
+        assert_close(gp[k], rp[k], REL_TOL, k + ' vs CPU oracle, B=1 256x832')
+    g = load_golden('step_b1_256x832.npz')
+    for k in rp:
+        assert_close(gp[k], g[k], REL_TOL, k + ' vs reference golden, B=1 256x832')
+    gv = torch.cat([p.grad.flatten().cpu() for p in m.parameters()])
+    rv = torch.cat([q.grad.flatten() for q in ref.parameters()])
+    assert float((gv - rv).norm() / rv.norm()) <= 3e-4          # mkldnn vs cuDNN convolutions
+    err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x)
+    assert noise <= NOISE_CAP, noise
+    assert err <= REL_TOL + noise, (err, noise)
 
 
 def test_inference_flow_matches_oracle(U):
@@ -225,6 +275,7 @@ def test_config4_sintel_shape_step(U):
     rv = torch.cat([q.grad.flatten() for q in ref.parameters()])
     assert float((gv - rv).norm() / rv.norm()) <= 3e-4          # CPU (mkldnn) vs GPU (cuDNN) convolutions differ by ~1e-4
     err, noise = global_grad_err_vs_same_gpu_oracle(m, ref, x[:1], w_smooth=6.0)
+    assert noise <= 2 * NOISE_CAP, 'run-to-run spread %.2e' % noise        # 459k pixels of sign-of-noise smoothness gradients
     assert err <= REL_TOL + noise, (err, noise)
     print('sintel-shape gradient: err vs same-GPU oracle %.2e, run-to-run spread %.2e' % (err, noise))
     m.zero_grad(set_to_none=True)

@@ -198,6 +198,55 @@ def test_warp_vs_oracle(U, shape, sigma, use_mask, ac):
     assert_close(gf, rf, REL_TOL, 'warp grad flow')
 
 
+# Shapes the bench times (B=8 triplets -> 2B=16 stacked samples): the four decoder levels that warp features
+# (pwc_tf.py:121,134,146,159) and the three image scales Model_flow.forward warps (model_flow_paper.py:233-235).
+WARP_LEVEL_SHAPES = [(16, 128, 8, 26), (16, 96, 16, 52), (16, 64, 32, 104), (16, 32, 64, 208)]
+WARP_IMAGE_SHAPES = [(16, 3, 64, 208), (16, 3, 128, 416), (16, 3, 256, 832)]
+
+
+def _warp_level_case(U, shape, sigma, use_mask, ac, need_gx):
+    """CUDA warp vs the oracle (ATen grid_sample) run on the SAME GPU -- the CPU oracle needs minutes at these sizes.
+    Values and both gradients at 1e-4; where the validity mask is used, pixels whose in-bounds weight sum lies within
+    1e-6 of the 0.9999 threshold may flip (different fp32 summation order), so the thresholded masks are required to agree
+    on >= 99.9 % of the pixels and values are compared where they do."""
+    g = torch.Generator().manual_seed(101 + sum(shape))
+    B, C, H, W = shape
+    x = torch.rand(shape, generator=g).cuda().requires_grad_(need_gx)
+    fl = flows_like(g, B, H, W, sigma).cuda().requires_grad_(True)
+    ct = torch.randn(shape, generator=g).cuda()
+    xr, fr = x.detach().clone().requires_grad_(need_gx), fl.detach().clone().requires_grad_(True)
+    ref = O.warp_flow(xr, fr, use_mask=use_mask, align_corners=ac)
+    out = U.warp_flow(x, fl, use_mask=use_mask, align_corners=ac)
+    assert out.shape == ref.shape
+    agree = torch.ones(B, 1, H, W, dtype=torch.bool, device='cuda')
+    if use_mask:
+        agree = ((out.detach() != 0).any(1, keepdim=True) == (ref.detach() != 0).any(1, keepdim=True))
+        assert float(agree.float().mean()) >= MASK_AGREE
+    ctm = ct * agree
+    assert_close(out.detach() * agree, ref.detach() * agree, REL_TOL, 'warp fwd %r' % (shape,))
+    ins_g, ins_r = ([x, fl], [xr, fr]) if need_gx else ([fl], [fr])
+    gg = torch.autograd.grad((out * ctm).sum(), ins_g)
+    gr = torch.autograd.grad((ref * ctm).sum(), ins_r)
+    for a, b, what in zip(gg, gr, ('x', 'flow') if need_gx else ('flow',)):
+        assert_close(a, b, REL_TOL, 'warp grad %s %r' % (what, shape))
+
+
+@pytest.mark.parametrize('ac', [False, True])
+@pytest.mark.parametrize('shape', WARP_LEVEL_SHAPES)
+def test_warp_decoder_level_shapes(U, shape, ac):
+    """a2 at the shapes of the B=8 256x832 step: the PXT / channel-chunk / row-map variants selected there, forward and
+    both gradients (the +gx backward with warp-aggregated REDs), decoder-sized flows plus an out-of-bounds column and row."""
+    _warp_level_case(U, shape, 1.5, False, ac, True)
+
+
+@pytest.mark.parametrize('ac', [False, True])
+@pytest.mark.parametrize('shape', WARP_IMAGE_SHAPES)
+def test_warp_image_scale_shapes(U, shape, ac):
+    """a3 at the three image scales of the B=8 256x832 step: validity mask on, gradient w.r.t. the flow only
+    (the images carry no gradient, model_flow_paper.py:62-66)."""
+    _warp_level_case(U, shape, 2.0 * shape[2] / 64, True, ac, False)
+
+
 def test_warp_golden(U):
     for tag in ('feat', 'img', 'wild'):
         for ac in (0, 1):

@@ -98,7 +98,7 @@ def test_losses_golden():
 
 
 def test_step_golden():
-    for tag, (B, H, W) in {'b1_64x128': (1, 64, 128), 'b2_64x64': (2, 64, 64)}.items():
+    for tag, (B, H, W) in {'b1_64x128': (1, 64, 128), 'b2_64x64': (2, 64, 64), 'b1_256x832': (1, 256, 832)}.items():
         g = load_golden('step_%s.npz' % tag)
         torch.manual_seed(0)
         m = omodel.Model_flow(omodel.Cfg)

@@ -28,13 +28,27 @@ def nvcc_path():
     return cand
 
 
+STAMP_PATH = LIB_PATH + '.stamp'
+
+
+def source_digest():
+    """sha256 over every file the library is built from (csrc/*, the public header, this recipe).  Stored next to the
+    .so so that staleness is decided by content, not by mtimes (a snapshot copied to another box has fresh mtimes)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    deps += [os.path.join(PKG, '..', 'include', 'uof_b200.h'), os.path.abspath(__file__)]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, '..', 'include', 'uof_b200.h'),
-                                                                os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP_PATH).read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -65,6 +79,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)
+    with open(STAMP_PATH, 'w') as f:
+        f.write(source_digest() + '\n')
     return LIB_PATH
 
 

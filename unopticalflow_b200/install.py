@@ -50,36 +50,52 @@ def _warp_pyramid(self, img_pyramid, flow_pyramid):
     return [ops.warp_flow(i, f, use_mask=True) for i, f in zip(img_pyramid, flow_pyramid)]
 
 
+_METHODS = (('compute_loss_flow_smooth', _smooth), ('compute_loss_flow_consis', _consis), ('generate_img_pyramid', _pyramid),
+            ('warp_flow_pyramid', _warp_pyramid), ('compute_diff_weight', _diff_weight), ('compute_loss_with_mask', _loss_with_mask))
+_saved = []          # (owner object, attribute name, original value) of everything install() rebound, for uninstall()
+
+
+def _rebind(owner, name, value):
+    _saved.append((owner, name, owner.__dict__.get(name) if isinstance(owner, type) else getattr(owner, name)))
+    setattr(owner, name, value)
+
+
 def install(modules=None, models=()):
     """Rebind every seam found in `modules` (default: sys.modules) and patch already-built `models`.
 
-    Returns the list of (module, name) pairs that were rebound so callers can verify the drop-in took."""
+    Returns the list of (module, name) pairs that were rebound so callers can verify the drop-in took;
+    `uninstall()` puts the reference's own callables back."""
     modules = sys.modules if modules is None else modules
     done = []
     for mod, name in _SEAMS:
         m = modules.get(mod)
         if m is not None and hasattr(m, name):
-            setattr(m, name, ops.warp_flow if name == 'warp_flow' else ops.SSIM)
+            _rebind(m, name, ops.warp_flow if name == 'warp_flow' else ops.SSIM)
             done.append((mod, name))
     pwc = modules.get('pwc_tf')
     if pwc is not None and hasattr(pwc, 'PWC_tf'):
-        pwc.PWC_tf.corr_naive = _corr_method            # picked up by `self.corr = self.corr_naive` (pwc_tf.py:19)
+        _rebind(pwc.PWC_tf, 'corr_naive', _corr_method)   # picked up by `self.corr = self.corr_naive` (pwc_tf.py:19)
         done.append(('pwc_tf', 'PWC_tf.corr_naive'))
     mfp = modules.get('model_flow_paper')
     if mfp is not None and hasattr(mfp, 'Model_flow'):
-        cls = mfp.Model_flow
-        cls.compute_loss_flow_smooth = _smooth
-        cls.compute_loss_flow_consis = _consis
-        cls.generate_img_pyramid = _pyramid
-        cls.warp_flow_pyramid = _warp_pyramid
-        cls.compute_diff_weight = _diff_weight
-        cls.compute_loss_with_mask = _loss_with_mask
-        done += [('model_flow_paper', 'Model_flow.' + n) for n in
-                 ('compute_loss_flow_smooth', 'compute_loss_flow_consis', 'generate_img_pyramid', 'warp_flow_pyramid',
-                  'compute_diff_weight', 'compute_loss_with_mask')]
+        for n, fn in _METHODS:
+            _rebind(mfp.Model_flow, n, fn)
+            done.append(('model_flow_paper', 'Model_flow.' + n))
     for model in models:                                 # instances built before install()
         inner = getattr(model, 'module', model)
         if hasattr(inner, 'pwc_model'):
-            inner.pwc_model.corr = ops.corr
+            _rebind(inner.pwc_model, 'corr', ops.corr)
             done.append((type(inner).__name__, 'pwc_model.corr'))
     return done
+
+
+def uninstall():
+    """Undo every rebinding made by install() (most recent first).  Returns how many were restored."""
+    n = len(_saved)
+    while _saved:
+        owner, name, orig = _saved.pop()
+        if orig is None and isinstance(owner, type):
+            delattr(owner, name)
+        else:
+            setattr(owner, name, orig)
+    return n
