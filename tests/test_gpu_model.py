@@ -168,7 +168,8 @@ def test_train_steps_track_oracle(U):
 
 
 def test_graphed_train_step_matches_eager(U):
-    """The CUDA-graph replay of the whole iteration (train.GraphedTrainStep) follows the eager trajectory."""
+    """The CUDA-graph replay of the whole iteration (train.GraphedTrainStep) follows the eager trajectory from the SAME
+    starting point: the constructor's warm-up iterations are undone (parameters and Adam state restored) before capture."""
     from unopticalflow_b200 import train as T
     torch.manual_seed(0)
     m1, m2 = U.Model_flow(T.KITTI_CFG).cuda(), U.Model_flow(T.KITTI_CFG).cuda()
@@ -177,13 +178,43 @@ def test_graphed_train_step_matches_eager(U):
     gen = torch.Generator().manual_seed(1234)
     xs = [torch.rand(2, 3, 192, 128, generator=gen).cuda() for _ in range(3)]
     opt = T.make_optimizer(m1)
-    graphed = T.GraphedTrainStep(m2, xs[0], w, warmup=3)          # three real warm-up steps on xs[0]; capture does not execute
-    for _ in range(3):
-        T.train_step(m1, opt, xs[0], w)
+    graphed = T.GraphedTrainStep(m2, xs[0], w, warmup=3)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert torch.equal(p, q), 'GraphedTrainStep construction moved the parameters'
+    assert all(float(st['step']) == 0 and float(st['exp_avg'].abs().max()) == 0 for st in graphed.optimizer.state.values())
     for i in range(4):
         le = float(T.train_step(m1, opt, xs[i % 3], w))
         lg = float(graphed(xs[i % 3]))
         assert abs(le - lg) <= 2e-4 * abs(le), (i, le, lg)
+
+
+def test_checkpoint_roundtrip_reference_layout(U, tmp_path):
+    """train.py:23-31: save_model / load_model with the reference's dict layout; resuming a graphed step from a checkpoint
+    (model + Adam state) continues the trajectory of the run that wrote it."""
+    from unopticalflow_b200 import train as T
+    torch.manual_seed(0)
+    w = T.generate_loss_weights_dict(T.KITTI_CFG)
+    gen = torch.Generator().manual_seed(7)
+    xs = [torch.rand(1, 3, 192, 128, generator=gen).cuda() for _ in range(4)]
+    m1 = U.Model_flow(T.KITTI_CFG).cuda()
+    run1 = T.GraphedTrainStep(m1, xs[0], w, warmup=2)
+    for i in range(2):
+        run1(xs[i])
+    T.save_model(1, str(tmp_path), 'last.pth', m1, run1)
+    data = torch.load(str(tmp_path / 'last.pth'))
+    assert set(data) == {'iteration', 'model_state_dict', 'optimizer_state_dict'} and len(data['model_state_dict']) == 98
+    expect = [float(run1(xs[i])) for i in (2, 3)]
+    m2 = U.Model_flow(T.KITTI_CFG).cuda()
+    run2 = T.GraphedTrainStep(m2, xs[0], w, warmup=2)
+    it, _, _ = T.load_model(str(tmp_path), 'last.pth', m2, run2)
+    assert it == 1
+    got = [float(run2(xs[i])) for i in (2, 3)]
+    for a, b in zip(got, expect):
+        assert abs(a - b) <= 2e-4 * abs(b), (got, expect)
+    # a DataParallel-style checkpoint ('module.' prefix, train.py:36-37) loads into the bare model
+    data['model_state_dict'] = {'module.' + k: v for k, v in data['model_state_dict'].items()}
+    torch.save(data, str(tmp_path / 'dp.pth'))
+    T.load_model(str(tmp_path), 'dp.pth', U.Model_flow(T.KITTI_CFG).cuda(), None)
 
 
 def test_graphed_step_staged_inputs_and_flat_gradients(U):

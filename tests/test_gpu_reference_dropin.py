@@ -100,3 +100,34 @@ def test_reference_class_with_cuda_seams(ref_networks, B, H, W):
     with torch.no_grad():
         stock(x[:1])
     assert _lib.launch_count() == n0
+
+
+def test_helper_methods_match_reference_class(ref_networks):
+    """The reference's helper methods that its own forward never calls (model_flow_paper.py:68-87 compute_loss_pixel /
+    _without_mask, :152-167 gradients / cal_grad2_error) exist on the product class with the same results."""
+    import unopticalflow_b200 as U
+    stock = ref_networks.get_model('flow')(omodel.Cfg).cuda()
+    prod = U.Model_flow(omodel.Cfg).cuda()
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 2, 32, 48
+    imgs = [torch.rand(B, 3, H >> s, W >> s, generator=g).cuda() for s in range(3)]
+    warped = [torch.rand(B, 3, H >> s, W >> s, generator=g).cuda().requires_grad_(True) for s in range(3)]
+    masks = [torch.rand(B, 1, H >> s, W >> s, generator=g).cuda() * 2 for s in range(3)]
+    flow = (torch.randn(B, 2, H, W, generator=g) * 3).cuda().requires_grad_(True)
+    ct = torch.randn(B, generator=g).cuda()
+    for name, args in (('compute_loss_pixel', (imgs, warped, masks)), ('compute_loss_pixel_without_mask', (imgs, warped)),
+                       ('cal_grad2_error', (flow, imgs[0]))):
+        r, p = getattr(stock, name)(*args), getattr(prod, name)(*args)
+        assert p.shape == r.shape == (B,)
+        assert_close(p, r, REL_TOL, name)
+        wrt = [flow] if name == 'cal_grad2_error' else warped
+        gr = torch.autograd.grad((r * ct).sum(), wrt)
+        gp = torch.autograd.grad((p * ct).sum(), wrt)
+        for a, b in zip(gp, gr):
+            assert_close(a, b, REL_TOL, name + ' gradient')
+    for a, b in zip(prod.gradients(imgs[0]), stock.gradients(imgs[0])):
+        assert torch.equal(a, b)
+    # forward kwargs of model_flow_paper.py:205 are accepted
+    x = torch.rand(1, 3, 192, 64, generator=g).cuda()
+    pack = prod(x, use_flow_loss=True, is_second_phase=False)
+    assert set(pack) == {'loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis'}

@@ -52,6 +52,17 @@ class Model_flow(nn.Module):
         reference, diffs differentiable w.r.t. the warped images."""
         return ops.diff_weight(img_pyramid_from_l, img_pyramid, img_pyramid_from_r, self.num_scales)
 
+    def compute_loss_pixel(self, img_pyramid, img_warped_pyramid, occ_mask_list):
+        """model_flow_paper.py:68-77 (not called by the reference's forward): masked mean of |img - warped| over 3 channels."""
+        diffs = [torch.abs(img_pyramid[s] - img_warped_pyramid[s]) for s in range(self.num_scales)]
+        return ops.loss_with_mask(diffs, occ_mask_list, self.num_scales)
+
+    def compute_loss_pixel_without_mask(self, img_pyramid, img_warped_pyramid):
+        """model_flow_paper.py:79-87 (not called by the reference's forward)."""
+        diffs = [torch.abs(img_pyramid[s] - img_warped_pyramid[s]) for s in range(self.num_scales)]
+        ones = [torch.ones_like(d[:, :1]) for d in diffs]
+        return ops.loss_with_mask(diffs, ones, self.num_scales) * (1.0 + 1e-12)      # the masked form divides by mean(1) + 1e-12
+
     def compute_loss_with_mask(self, diff_list, occ_mask_list):
         return ops.loss_with_mask(diff_list, occ_mask_list, self.num_scales)
 
@@ -62,6 +73,15 @@ class Model_flow(nn.Module):
             s_map = ops.SSIM(img * m, wp * m)
             total = total + torch.clamp((1.0 - s_map) / 2.0, 0, 1).mean((1, 2, 3)) / (m.mean((1, 2, 3)) + 1e-12)
         return total
+
+    def gradients(self, img):
+        """model_flow_paper.py:152-155: forward differences (dx, dy)."""
+        return img[:, :, :, 1:] - img[:, :, :, :-1], img[:, :, 1:, :] - img[:, :, :-1, :]
+
+    def cal_grad2_error(self, flow, img):
+        """model_flow_paper.py:157-167: edge-aware second-order smoothness of ONE level, (B,).  The fused kernel computes the
+        reference's `cal_grad2_error(flow / 20, img)` (compute_loss_flow_smooth); the factor is undone on the way in."""
+        return ops.flow_smooth_loss([flow * 20.0], [img], 1)
 
     def compute_loss_flow_smooth(self, optical_flows, img_pyramid):
         return ops.flow_smooth_loss(optical_flows, img_pyramid, self.num_scales)
@@ -85,7 +105,10 @@ class Model_flow(nn.Module):
         return self.pwc_model([f[:B] for f in feats], [f[B:] for f in feats], [img1.shape[2], img1.shape[3]])[0]
 
     # ---- training step ----------------------------------------------------------------------------------
-    def forward(self, inputs, output_flow=False):
+    def forward(self, inputs, output_flow=False, use_flow_loss=True, is_second_phase=False):
+        """model_flow_paper.py:205-255.  `use_flow_loss` / `is_second_phase` are accepted and ignored, as the reference's
+        forward does (it never reads them); `output_flow=True` additionally returns the forward and backward flow pyramids
+        (the reference accepts the flag and returns the loss pack only)."""
         assert inputs.shape[1] == 3
         B, H, W = inputs.shape[0], int(inputs.shape[2] / 3), inputs.shape[3]
         S = self.num_scales

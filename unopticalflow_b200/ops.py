@@ -32,6 +32,21 @@ def _require_cuda(*tensors):
             raise TypeError('unopticalflow_b200 operators are fp32 only (got %s)' % t.dtype)
 
 
+def _alert_not_deterministic(what):
+    """Mirror of ATen's `globalContext().alertNotDeterministic`: the kernels named here combine partial results with fp32
+    atomics (per-block `RED`s of the fused loss sums, the scattered d/dx of the warp, the splat, split-K > 8 of the cost
+    volume), so their last bits depend on the order the blocks retire.  Under `torch.use_deterministic_algorithms(True)`
+    that is an error (a warning with `warn_only=True`), exactly like `grid_sampler_2d_backward_cuda` in the reference path."""
+    if torch.are_deterministic_algorithms_enabled():
+        msg = ('%s does not have a deterministic implementation (fp32 atomics), but you set '
+               "'torch.use_deterministic_algorithms(True)'." % what)
+        if torch.is_deterministic_algorithms_warn_only_enabled():
+            import warnings
+            warnings.warn(msg)
+        else:
+            raise RuntimeError(msg)
+
+
 def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -138,6 +153,8 @@ class _WarpFlow(torch.autograd.Function):
         B, C, H, W = xc.shape
         gout = gout.contiguous(memory_format=torch.channels_last) if cl else gout.contiguous()
         gx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        if gx is not None:
+            _alert_not_deterministic('uof_warp_bwd (gradient w.r.t. the warped tensor)')
         gflow = torch.empty_like(fc)
         with torch.cuda.device_of(xc):
             _lib.call('uof_warp_bwd', _p(gout), _p(xc), _p(fc), _p(gx), _p(gflow), B, C, H, W, use_mask, align_corners,
@@ -214,17 +231,18 @@ class _PhotoLoss(torch.autograd.Function):
         for s in range(S):
             _, _, H, W = imgs[s].shape
             assert wl[s].shape == imgs[s].shape and wr[s].shape == imgs[s].shape and imgs[s].shape[1] == 3
-            weights_l.append(torch.empty((B, 1, H, W), device=dev))
-            weights_r.append(torch.empty((B, 1, H, W), device=dev))
+            weights_l.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+            weights_r.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
             if want_diff:
-                diffs_l.append(torch.empty((B, 1, H, W), device=dev))
-                diffs_r.append(torch.empty((B, 1, H, W), device=dev))
+                diffs_l.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+                diffs_r.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
             lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(),
                                weights_l[s].data_ptr(), weights_r[s].data_ptr(),
                                diffs_l[s].data_ptr() if want_diff else None, diffs_r[s].data_ptr() if want_diff else None,
                                None, None, H, W)
-        sums = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, device=dev)      # (S,B,6) partial sums + the kernel's block counter
-        loss_pixel, loss_ssim = torch.empty(B, device=dev), torch.empty(B, device=dev)
+        _alert_not_deterministic('uof_photo_loss_fwd')
+        sums = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, device=dev, dtype=torch.float32)      # (S,B,6) partial sums + the kernel's block counter
+        loss_pixel, loss_ssim = torch.empty(B, device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
         with torch.cuda.device_of(imgs[0]):
             _lib.call('uof_photo_loss_fwd', lv, S, B, _p(sums), _p(loss_pixel), _p(loss_ssim), _stream(imgs[0]))
         # the weight maps are saved too: with them the backward kernel skips the weight math (split variant)
@@ -258,8 +276,8 @@ class _PhotoLoss(torch.autograd.Function):
             _, _, H, W = imgs[s].shape
             lv[s] = PhotoLevel(imgs[s].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), wmaps[s].data_ptr(),
                                wmaps[S + s].data_ptr(), None, None, gl[s].data_ptr(), gr[s].data_ptr(), H, W)
-        g_pixel = torch.zeros(B, device=sums.device) if g_pixel is None else g_pixel.contiguous()
-        g_ssim = torch.zeros(B, device=sums.device) if g_ssim is None else g_ssim.contiguous()
+        g_pixel = torch.zeros(B, device=sums.device, dtype=torch.float32) if g_pixel is None else g_pixel.contiguous()
+        g_ssim = torch.zeros(B, device=sums.device, dtype=torch.float32) if g_ssim is None else g_ssim.contiguous()
         with torch.cuda.device_of(sums):
             _lib.call('uof_photo_loss_bwd', lv, S, B, _p(sums), _p(g_pixel), _p(g_ssim), _stream(sums))
         if stacked:
@@ -301,7 +319,7 @@ class _DiffWeight(torch.autograd.Function):
     def forward(ctx, img, wl, wr):
         img, wl, wr = img.contiguous(), wl.contiguous(), wr.contiguous()
         B, _, H, W = img.shape
-        outs = [torch.empty((B, 1, H, W), device=img.device) for _ in range(4)]
+        outs = [torch.empty((B, 1, H, W), device=img.device, dtype=torch.float32) for _ in range(4)]
         with torch.cuda.device_of(img):
             _lib.call('uof_diff_weight_fwd', _p(img), _p(wl), _p(wr), *[_p(t) for t in outs], B, H, W, _stream(img))
         ctx.save_for_backward(img, wl, wr)
@@ -344,7 +362,8 @@ class _MaskedMean(torch.autograd.Function):
         arr = lambda ts: (ctypes.c_void_p * S)(*[t.data_ptr() for t in ts])
         Hs = (ctypes.c_int * S)(*[d.shape[2] for d in diffs])
         Ws = (ctypes.c_int * S)(*[d.shape[3] for d in diffs])
-        sums, loss = torch.empty((S, B, 2), device=dev), torch.empty(B, device=dev)
+        sums, loss = torch.empty((S, B, 2), device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
+        _alert_not_deterministic('uof_masked_mean_fwd')
         with torch.cuda.device_of(diffs[0]):
             _lib.call('uof_masked_mean_fwd', arr(diffs), arr(masks), Hs, Ws, S, B, C, _p(sums), _p(loss), _stream(diffs[0]))
         ctx.save_for_backward(sums, *diffs, *masks)
@@ -383,11 +402,17 @@ class _SmoothLoss(torch.autograd.Function):
         B, Bimg = flows[0].shape[0], imgs[0].shape[0]
         dev = flows[0].device
         lv = _levels(SmoothLevel, S)
+        if Bimg <= 0 or B % Bimg:
+            raise ValueError('flow_smooth_loss: the flow batch %d must be a multiple of the image batch %d' % (B, Bimg))
         for s in range(S):
             _, _, H, W = flows[s].shape
-            assert imgs[s].shape[2:] == flows[s].shape[2:]
+            # the kernels hard-code 2 flow and 3 image channels and index the image with the flow's sizes
+            if tuple(flows[s].shape) != (B, 2, H, W) or tuple(imgs[s].shape) != (Bimg, 3, H, W):
+                raise ValueError('flow_smooth_loss level %d: flow %r must be (B,2,H,W) and img %r (B_img,3,H,W) of the same size'
+                                 % (s, tuple(flows[s].shape), tuple(imgs[s].shape)))
             lv[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), None, H, W)
-        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev)
+        _alert_not_deterministic('uof_smooth_loss_fwd')
+        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
         with torch.cuda.device_of(flows[0]):
             _lib.call('uof_smooth_loss_fwd', lv, S, B, Bimg, _p(sums), _p(loss), _stream(flows[0]))
         ctx.save_for_backward(*flows, *imgs)
@@ -430,8 +455,14 @@ class _ConsisLoss(torch.autograd.Function):
         lv = _levels(ConsisLevel, S)
         for s in range(S):
             _, _, H, W = ff[s].shape
+            # the kernel indexes flow_bwd and weight_fwd with flow_fwd's sizes: a weight map of another level would be an
+            # out-of-bounds device read, so refuse what the reference would have broadcast or rejected
+            if tuple(ff[s].shape) != (B, 2, H, W) or fb[s].shape != ff[s].shape or tuple(wf[s].shape) != (B, 1, H, W):
+                raise ValueError('flow_consis_loss level %d: fwd flow %r, bwd flow %r must both be (B,2,H,W) and the weight %r (B,1,H,W)'
+                                 % (s, tuple(ff[s].shape), tuple(fb[s].shape), tuple(wf[s].shape)))
             lv[s] = ConsisLevel(ff[s].data_ptr(), fb[s].data_ptr(), wf[s].data_ptr(), None, H, W)
-        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev)
+        _alert_not_deterministic('uof_consis_loss_fwd')
+        sums, loss = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
         with torch.cuda.device_of(ff[0]):
             _lib.call('uof_consis_loss_fwd', lv, S, B, _p(sums), _p(loss), _stream(ff[0]))
         ctx.save_for_backward(sums, *ff, *fb, *wf)
@@ -506,6 +537,7 @@ class _BiasLeakyReLU(torch.autograd.Function):
             g2 = g2.contiguous()
         gx = torch.empty_like(y)
         gbias = torch.empty(C, device=y.device, dtype=torch.float32)
+        _alert_not_deterministic('uof_bias_lrelu_bwd (bias gradient)')
         with torch.cuda.device_of(y):
             _lib.call('uof_bias_lrelu_bwd2', _p(g1), g1.stride(0), _p(g2) if g2 is not None else None,
                       g2.stride(0) if g2 is not None else 0, _p(y), _p(gx), _p(gbias), B, C, H, W, ctx.slope, _stream(y))
@@ -553,7 +585,8 @@ def upsample_bilinear_scaled(x: torch.Tensor, size, scale: float = 1.0) -> torch
 
 # ------------------------------------------------------------------------------------------ a9
 def _pyramid_launch(base, nimg, stride_img, B, C, H, W, sb, sc, sh, num_pyramid):
-    lv = [torch.empty((nimg, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=base.device) for s in range(1, num_pyramid)]
+    lv = [torch.empty((nimg, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=base.device, dtype=torch.float32)
+          for s in range(1, num_pyramid)]
     ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
     with torch.cuda.device_of(base):
         _lib.call('uof_img_pyramid', _p(base), stride_img, sb, sc, sh, ptrs, num_pyramid, nimg, B, C, H, W, _stream(base))
@@ -612,8 +645,8 @@ def img_pyramid_triplet_stacked(inputs: torch.Tensor, num_pyramid: int):
     if (x.stride(3) != 1 or H3 % 3 or H % 4 or W % 4 or not 2 <= num_pyramid <= 3 or x.data_ptr() % 16
             or any(st % 4 for st in (H * x.stride(2), x.stride(0), x.stride(1), x.stride(2)))):
         return None
-    lv0 = torch.empty((3, B, C, H, W), device=x.device)
-    lv = [torch.empty((3, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=x.device) for s in range(1, num_pyramid)]
+    lv0 = torch.empty((3, B, C, H, W), device=x.device, dtype=torch.float32)
+    lv = [torch.empty((3, B, C, int(H / 2 ** s), int(W / 2 ** s)), device=x.device, dtype=torch.float32) for s in range(1, num_pyramid)]
     ptrs = (ctypes.c_void_p * len(lv))(*[t.data_ptr() for t in lv])
     slots = (ctypes.c_int * 3)(*TRIPLET_SLOTS)
     with torch.cuda.device_of(x):
@@ -630,7 +663,8 @@ class _Splat(torch.autograd.Function):
         B, H, W, _ = fc.shape
         uc = u.contiguous() if u is not None else None
         C = uc.shape[3] if uc is not None else 1
-        out = torch.empty((B, H, W, C), device=fc.device)
+        out = torch.empty((B, H, W, C), device=fc.device, dtype=torch.float32)
+        _alert_not_deterministic('uof_splat_fwd')
         with torch.cuda.device_of(fc):
             _lib.call('uof_splat_fwd', _p(uc), _p(fc), _p(out), B, H, W, C, _stream(fc))
         ctx.save_for_backward(fc, *(() if uc is None else (uc,)))
@@ -693,7 +727,7 @@ def fb_consistency_mask(flow_fwd, flow_rev, alpha=3.0, beta=0.05, align_corners=
     ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
     ff, fr = flow_fwd.detach().contiguous(), flow_rev.detach().contiguous()
     B, _, H, W = ff.shape
-    mask = torch.empty((B, 1, H, W), device=ff.device)
+    mask = torch.empty((B, 1, H, W), device=ff.device, dtype=torch.float32)
     with torch.cuda.device_of(ff):
         _lib.call('uof_fb_consistency_mask', _p(ff), _p(fr), _p(mask), B, H, W, float(alpha), float(beta), int(ac), _stream(ff))
     return mask

@@ -29,10 +29,53 @@ def total_loss(loss_pack, weights):
     return torch.stack([weights[k] * loss_pack[k].mean() for k in loss_pack]).sum()
 
 
+def trainable_parameters(model):
+    """The parameters train.py:39 hands to Adam.  `Model_flow` freezes everything in 'depth' / 'flowposenet' mode
+    (model_flow_paper.py:19-24); an empty list is reported as such instead of an IndexError further down."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    if not params:
+        raise ValueError('the model has no trainable parameters (cfg.mode freezes Model_flow in depth / flowposenet mode): '
+                         'nothing to optimise')
+    return params
+
+
 def make_optimizer(model, lr=1e-4, fused=True):
     """train.py:39 -- Adam with default betas/eps; `fused` uses the single-launch multi-tensor CUDA Adam."""
-    params = [p for p in model.parameters() if p.requires_grad]
+    params = trainable_parameters(model)
     return torch.optim.Adam([{'params': params, 'lr': lr}], fused=fused and params[0].is_cuda)
+
+
+def _strip_prefix(state_dict):
+    """Checkpoint keys without the wrappers the reference may have saved them under: `module.` (DataParallel / DDP,
+    train.py:36-37) and `model_flow.` / `model_pose.model_flow.` (the upstream multi-task models, train.py:52-58)."""
+    out = {}
+    for k, v in state_dict.items():
+        for pre in ('module.', 'model_pose.', 'model_flow.'):
+            if k.startswith(pre):
+                k = k[len(pre):]
+        out[k] = v
+    return out
+
+
+def save_model(iter_, model_dir, filename, model, optimizer):
+    """train.py:23-24: {'iteration', 'model_state_dict', 'optimizer_state_dict'} -- the reference's checkpoint layout, so its
+    `iter_N.pth` / `last.pth` files and ours are interchangeable.  `optimizer` may be a torch optimizer or a
+    `GraphedTrainStep` (both have `state_dict()`)."""
+    import os
+    inner = getattr(model, 'module', model)
+    torch.save({'iteration': iter_, 'model_state_dict': inner.state_dict(), 'optimizer_state_dict': optimizer.state_dict()},
+               os.path.join(model_dir, filename))
+
+
+def load_model(model_dir, filename, model, optimizer=None, map_location=None):
+    """train.py:26-31 (+ the prefix renaming of :50-60, in reverse): returns (iteration, model, optimizer)."""
+    import os
+    data = torch.load(os.path.join(model_dir, filename), map_location=map_location)
+    inner = getattr(model, 'module', model)
+    inner.load_state_dict(_strip_prefix(data['model_state_dict']))
+    if optimizer is not None and data.get('optimizer_state_dict') is not None:
+        optimizer.load_state_dict(data['optimizer_state_dict'])
+    return data['iteration'], model, optimizer
 
 
 class FlatGradAllReduce:
@@ -47,6 +90,8 @@ class FlatGradAllReduce:
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('FlatGradAllReduce: no trainable parameters')
         n = sum(p.numel() for p in self.params)
         p0 = self.params[0]
         self.flat = torch.zeros(n, dtype=p0.dtype, device=p0.device)
@@ -74,24 +119,67 @@ class GraphedTrainStep:
     `allreduce=True` (one process per GPU, torch.distributed initialised with NCCL): gradients live in one flat buffer
     and are averaged over the ranks by a single captured NCCL all-reduce between backward and Adam
     (`FlatGradAllReduce`) -- the data-parallel step of SURVEY 8e without DDP's host-side hooks.
-    `forward_module` lets the captured forward go through a wrapper of `model`."""
+    `forward_module` lets the captured forward go through a wrapper of `model`.
 
-    def __init__(self, model, inputs_like, weights, lr=1e-4, warmup=3, forward_module=None, allreduce=False, group=None):
-        params = [p for p in model.parameters() if p.requires_grad]
+    The eager warm-up iterations (cuDNN autotune, lazy initialisation) are REAL optimiser steps on `inputs_like`; the
+    parameters and the Adam state are snapshotted before them and restored before capture, so constructing the step does
+    not move the training trajectory, and `optimizer_state` (an Adam `state_dict()`, e.g. the `optimizer_state_dict` of a
+    reference checkpoint) is loaded after the warm-up, i.e. it is what the first replay starts from."""
+
+    def __init__(self, model, inputs_like, weights, lr=1e-4, warmup=3, forward_module=None, allreduce=False, group=None,
+                 optimizer_state=None):
+        params = trainable_parameters(model)
         self.model, self.weights = (forward_module if forward_module is not None else model), weights
         self.optimizer = torch.optim.Adam([{'params': params, 'lr': lr}], fused=True, capturable=True)
         self.exchange = FlatGradAllReduce(params, group) if allreduce else None
         self.static_in = torch.empty_like(inputs_like)
         self.static_in.copy_(inputs_like)
+        saved_params = [p.detach().clone() for p in params]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # eager warm-up on a side stream (cuDNN autotune, lazy inits)
             for _ in range(warmup):
                 self._eager()
+            # undo the warm-up: parameters back to their values, Adam moments and step counters back to zero -- in place,
+            # the graph is captured on these very tensors
+            with torch.no_grad():
+                for p, q in zip(params, saved_params):
+                    p.copy_(q)
+                for st in self.optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
         torch.cuda.current_stream().wait_stream(side)
+        del saved_params
+        if optimizer_state is not None:
+            self.load_state_dict(optimizer_state)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager()
+
+    def state_dict(self):
+        """The Adam state (`optimizer_state_dict` of the reference's checkpoints, train.py:24)."""
+        return self.optimizer.state_dict()
+
+    def load_state_dict(self, state):
+        """Load an Adam state IN PLACE: the captured graph reads the moment / step tensors it was captured on, so the
+        values are copied into them (`step` may arrive as a Python number or a CPU tensor from a non-capturable Adam)."""
+        if not self.optimizer.state:                       # no warm-up ran: let torch build the state, capturable layout
+            self.optimizer.load_state_dict(state)
+            return
+        params = self.optimizer.param_groups[0]['params']
+        packed = state['state']
+        with torch.no_grad():
+            for i, p in enumerate(params):
+                src = packed.get(i, packed.get(str(i)))
+                if src is None:
+                    continue
+                dst = self.optimizer.state[p]
+                for k, v in src.items():
+                    if torch.is_tensor(dst.get(k)):
+                        dst[k].copy_(torch.as_tensor(v, dtype=dst[k].dtype))
+                    else:
+                        dst[k] = v
 
     def _eager(self):
         if self.exchange is not None:
