@@ -55,8 +55,14 @@ int uof_cost_volume_bwd(const float* gout, long long gout_batch_stride,
  * normalisation, grid_sample(zeros padding) and, with use_mask, the validity mask
  * (sum of in-bounds corner weights >= 0.9999, net_utils.py:47-52) in ONE kernel.
  * x,out: (B,C,H,W) NCHW, or NHWC storage when channels_last != 0 (C % 4 == 0 required);
- * flow: (B,2,H,W) NCHW always.  align_corners selects the grid_sample convention
- * (0 = installed torch default, 1 = torch-1.2 behaviour). */
+ * flow: (B,2,H,W) NCHW always.  align_corners is a flags word: bit 0 selects the grid_sample
+ * convention (0 = installed torch default, 1 = torch-1.2 behaviour); bit 1
+ * (UOF_COORD_HOST) selects the fp32 rounding of the coordinate chain: clear = ATen's CUDA kernels
+ * (reciprocal multiply + FMA, what the reference computes on a GPU), set = ATen's CPU kernels
+ * (true division, no contraction: the CPU oracle's arithmetic).  The two differ by one ulp of the
+ * normalised coordinate, i.e. up to 1e-4 relative in the flow gradient at W ~ 800. */
+#define UOF_ALIGN_CORNERS 1
+#define UOF_COORD_HOST 2
 int uof_warp_fwd(const float* x, const float* flow, float* out,
                  int B, int C, int H, int W, int use_mask, int align_corners,
                  int channels_last, uof_stream_t stream);

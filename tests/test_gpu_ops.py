@@ -247,6 +247,47 @@ def test_warp_image_scale_shapes(U, shape, ac):
     _warp_level_case(U, shape, 2.0 * shape[2] / 64, True, ac, False)
 
 
+def test_warp_coordinate_arithmetic_modes(U):
+    """The fp32 rounding of the sampling-coordinate chain is part of the reference's result: ATen's CUDA
+    kernels multiply by a reciprocal and contract an FMA, its CPU kernels divide.  At 256x832 the flow gradient of the
+    reference differs by ~1e-4 between the two devices; the kernels implement both roundings (`ops.COORD_ARITHMETIC`):
+    'cuda' (default) must follow the oracle executed on the GPU, 'host' the oracle executed on the CPU, each several
+    times closer than the two oracles are to each other."""
+    from unopticalflow_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(1, 3, 256, 832, generator=g)
+    fl = (torch.randn(1, 2, 256, 832, generator=g) * 2).requires_grad_(True)
+    ct = torch.randn(1, 3, 256, 832, generator=g)
+
+    def oracle_grad(dev):
+        f = fl.detach().to(dev).requires_grad_(True)
+        return torch.autograd.grad((O.warp_flow(x.to(dev), f) * ct.to(dev)).sum(), f)[0].cpu()
+
+    def ours(mode):
+        old, ops.COORD_ARITHMETIC = ops.COORD_ARITHMETIC, mode
+        try:
+            f = fl.detach().cuda().requires_grad_(True)
+            return torch.autograd.grad((U.warp_flow(x.cuda(), f) * ct.cuda()).sum(), f)[0].cpu()
+        finally:
+            ops.COORD_ARITHMETIC = old
+
+    def l2(a, b):
+        return float((a - b).norm() / b.norm())
+    g_cpu, g_gpu = oracle_grad('cpu'), oracle_grad('cuda')
+    across = l2(g_gpu, g_cpu)
+    e_cuda, e_host = l2(ours('cuda'), g_gpu), l2(ours('host'), g_cpu)
+    print('flow-gradient rel L2: oracle GPU vs CPU %.2e | kernel[cuda] vs GPU oracle %.2e | kernel[host] vs CPU oracle %.2e'
+          % (across, e_cuda, e_host))
+    assert e_cuda <= 2e-5 and e_host <= 2e-5
+    assert e_cuda < across / 3 and e_host < across / 3
+    with pytest.raises(ValueError):
+        ops.COORD_ARITHMETIC = 'nearest'
+        try:
+            U.warp_flow(x.cuda(), fl.detach().cuda())
+        finally:
+            ops.COORD_ARITHMETIC = 'cuda'
+
+
 def test_warp_golden(U):
     for tag in ('feat', 'img', 'wild'):
         for ac in (0, 1):

@@ -116,19 +116,39 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ---- bilinear sampling coordinates of warp_flow (net_utils.py:39-46 + ATen grid_sampler) ---------
-// Same fp32 operation order as the reference so that floor() lands on the same integer:
 //   v = x + fx;  g = 2*v/max(W-1,1) - 1;  ix = ((g+1)*W - 1)/2        (align_corners = False)
 //                                          ix = (g+1)/2*(W-1)          (align_corners = True)
-// __f*_rn intrinsics keep ptxas from contracting the chain into FMAs.
-__device__ __forceinline__ float sample_coord(float pos, float f, int size, bool align_corners) {
-  float v = __fadd_rn(pos, f);
-  float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)max(size - 1, 1)), 1.0f);
-  // (x / 2) == (x * 0.5f) exactly in binary floating point
-  if (align_corners) return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
-  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 0.5f);
+// The fp32 rounding of this chain is part of the reference's result: at x ~ 800 one ulp of g is 2.5e-5 px of ix, the
+// bilinear weights inherit it, and the gradient w.r.t. the flow (a difference of corner values times those weights) moves
+// by ~1e-4 relative -- the reference run on a CPU and the same reference run on a GPU differ by 1.15e-4 in the parameter
+// gradient at 256x832 for exactly this reason.  Both roundings are therefore implemented, selected by
+// bit 1 of the `align_corners` flags word of the C ABI:
+//   UOF_COORD_CUDA (default, bit clear): what ATen's CUDA kernels compute, i.e. what train.py runs --
+//     `/ (W-1)` of a tensor by a CPU scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), and
+//     grid_sampler_unnormalize's `(g+1)*W - 1` is contracted into one FMA by nvcc;
+//   UOF_COORD_HOST (bit set): what ATen's CPU kernels compute -- a true division and no contraction; this is the
+//     arithmetic of the CPU oracle and of the golden fixtures, used where floor() must land on the same integer.
+// __f*_rn intrinsics keep ptxas from (re)contracting the chain.
+constexpr int kAlignCorners = 1, kCoordHost = 2;
+__device__ __forceinline__ float sample_coord(float pos, float f, int size, int flags) {
+  const float v = __fadd_rn(pos, f);
+  const float denom = (float)max(size - 1, 1);
+  float g, ix;
+  if (flags & kCoordHost) {
+    g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), denom), 1.0f);
+    // (x / 2) == (x * 0.5f) exactly in binary floating point
+    if (flags & kAlignCorners) return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    ix = __fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f);
+  } else {
+    g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, v), __frcp_rn(denom)), 1.0f);
+    if (flags & kAlignCorners) return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    ix = __fmaf_rn(__fadd_rn(g, 1.0f), (float)size, -1.0f);
+  }
+  return __fmul_rn(ix, 0.5f);
 }
 // d(ix)/d(flow) for the mapping above.
-inline float coord_scale(int size, bool align_corners) {
+inline float coord_scale(int size, int flags) {
+  const bool align_corners = (flags & 1) != 0;
   float dg = 2.0f / (float)(size - 1 > 1 ? size - 1 : 1);
   return align_corners ? dg * 0.5f * (float)(size - 1) : dg * 0.5f * (float)size;
 }

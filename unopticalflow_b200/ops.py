@@ -18,6 +18,17 @@ from ._lib import ConsisLevel, PhotoLevel, SmoothLevel
 
 # grid_sample convention of "the reference executed under the installed torch" (SURVEY F4).
 DEFAULT_ALIGN_CORNERS = False
+# fp32 rounding of the sampling-coordinate chain (include/uof_b200.h, UOF_COORD_HOST): 'cuda' = what ATen's CUDA kernels
+# compute (the reference as train.py runs it: reciprocal multiply + FMA), 'host' = what ATen's CPU kernels compute (true
+# division; the arithmetic of the CPU oracle and the golden fixtures).  One ulp of the normalised coordinate apart, which at
+# W ~ 800 is 2.5e-5 px and ~1e-4 relative in the flow gradient -- as far as the reference is from itself across devices.
+COORD_ARITHMETIC = 'cuda'
+
+
+def _coord_flags(align_corners):
+    if COORD_ARITHMETIC not in ('cuda', 'host'):
+        raise ValueError("ops.COORD_ARITHMETIC must be 'cuda' or 'host'")
+    return (1 if align_corners else 0) | (2 if COORD_ARITHMETIC == 'host' else 0)
 NUM_DISPLACEMENTS = 81
 
 
@@ -140,10 +151,10 @@ class _WarpFlow(torch.autograd.Function):
         B, C, H, W = xc.shape
         out = torch.empty_like(xc)     # preserves the memory format
         with torch.cuda.device_of(xc):
-            _lib.call('uof_warp_fwd', _p(xc), _p(fc), _p(out), B, C, H, W, int(use_mask), int(align_corners), int(cl),
+            _lib.call('uof_warp_fwd', _p(xc), _p(fc), _p(out), B, C, H, W, int(use_mask), _coord_flags(align_corners), int(cl),
                       _stream(xc))
         ctx.save_for_backward(xc, fc)
-        ctx.flags = (int(use_mask), int(align_corners), int(cl))
+        ctx.flags = (int(use_mask), _coord_flags(align_corners), int(cl))
         return out
 
     @staticmethod
@@ -729,5 +740,5 @@ def fb_consistency_mask(flow_fwd, flow_rev, alpha=3.0, beta=0.05, align_corners=
     B, _, H, W = ff.shape
     mask = torch.empty((B, 1, H, W), device=ff.device, dtype=torch.float32)
     with torch.cuda.device_of(ff):
-        _lib.call('uof_fb_consistency_mask', _p(ff), _p(fr), _p(mask), B, H, W, float(alpha), float(beta), int(ac), _stream(ff))
+        _lib.call('uof_fb_consistency_mask', _p(ff), _p(fr), _p(mask), B, H, W, float(alpha), float(beta), _coord_flags(ac), _stream(ff))
     return mask
