@@ -305,6 +305,7 @@ extern "C" int uof_cost_volume_bwd(const float* gout, long long gout_batch_strid
   UOF_REQUIRE(gout_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_bwd: gout_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = 0;
+  if (cv::bwd_tc(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;      // tcgen05 banded GEMM
   if (cv::bwd_tma(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);

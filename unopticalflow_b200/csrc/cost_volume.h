@@ -55,5 +55,9 @@ bool fwd_tma(const float* f1, const float* f2, float* out, int B, int C, int H, 
 bool bwd_tma(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
              int H, int W, cudaStream_t stream, int* rc);
 
+// Tensor-core (tcgen05 + TMEM) backward, cost_volume_tc.cu.  Same contract as bwd_tma.
+bool bwd_tc(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
+            int H, int W, cudaStream_t stream, int* rc);
+
 }  // namespace cv
 }  // namespace uof
