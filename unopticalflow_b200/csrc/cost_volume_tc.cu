@@ -40,43 +40,71 @@ namespace {
 constexpr int TH = 16, TW = 8;                  // pixel tile (M = 128)
 constexpr int QH = TH + 2 * RAD, QW = TW + 2 * RAD;   // 24 x 16 window
 constexpr int NDISP = ND * ND;                  // 81
-constexpr int kTcThreads = 192;                 // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: converters / epilogue
+constexpr int kGroups = 3;                      // converter groups (4 warps each), window row c is built by group c % kGroups
+constexpr int kConvThreads = 128 * kGroups;
+constexpr int kTcThreads = 64 + kConvThreads;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: converters / epilogue
 constexpr int kGBytes = NDISP * TH * TW * 4;    // one gout tile: 41 472 B
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int C>
 struct TcCfg {
-  static constexpr int kStages = C <= 32 ? 3 : 4;
-  static constexpr int kTileBytes = C * QW * 4;                        // one [C][16] operand tile (C * 64 B, multiple of 512)
-  static constexpr int kStageBytes = 4 * kTileBytes;                   // role x {hi, lo}
+  // A "stage" is one window row (16 columns of K) of BOTH roles: two band-matrix chunks in TMEM ({hi, lo} x 16 columns each)
+  // and two feature tiles in shared memory (hi by TMA, lo by the converters).
+  //
+  // What bounds the kernel (ncu, profiles/r2_tc_bwd_*):
+  //  * A tcgen05.mma with A in TMEM re-reads its 128 x 8 x 4 B A tile for every instruction while the math of an M=128,
+  //    N=32, K=8 tf32 MMA is only 16 cycles.  For C <= 64 the hi and lo halves of a feature tile therefore sit in ONE
+  //    shared-memory operand of 2C rows ([B_hi ; B_lo]): A_hi * [B_hi ; B_lo]^T is one MMA of N = 2C into accumulator columns
+  //    [0, 2C), A_lo * B_hi^T a second one of N = C into [0, C), and the epilogue adds the halves: two A reads per K-step
+  //    instead of three.
+  //  * The converters.  With four converter warps (one per scheduler, nothing to switch to) every LDS / ALU dependency of
+  //    the ~300-instruction chunk construction was exposed and a row took ~1000 cycles whatever the ring depth (v1-v4:
+  //    0.64-0.78x of the CUDA-core kernel with the tensor pipe < 40 % busy).  Three converter groups work on three
+  //    different rows at a time (three warps per scheduler) and both roles of a row share the band predicates and addresses.
+  static constexpr bool kStack = C <= 64;
+  static constexpr int kDCols = kStack ? 2 * C : C;                    // accumulator columns per role
   static constexpr int kACols = 64;                                    // per stage: role x {hi, lo} x 16 columns
-  static constexpr int kTmemCols = 2 * C + kStages * kACols <= 256 ? 256 : 512;
-  static constexpr size_t kSmem = 1024 + 2 * (size_t)kGBytes + (size_t)kStages * kStageBytes + 256;
+  //  * TMA latency.  A feature row is 2 x C box rows of 64 bytes, one per channel plane: ~2-3 us from issue to the
+  //    mbarrier under load (v5: the converters spent 20 % of their time waiting for it with a 6-deep ring).  The shared-memory
+  //    ring (kNB rows of {[B_hi ; B_lo]} x 2 roles, freed by the MMA commit) is therefore deeper than the TMEM ring of band
+  //    chunks (kNS), which only bridges converters -> MMA.
+  static constexpr int kNS = (512 - 2 * kDCols) / kACols < 6 ? (512 - 2 * kDCols) / kACols : 6;      // TMEM ring depth
+  static constexpr int kNB = C <= 32 ? 12 : (C <= 64 ? 8 : (C <= 96 ? 5 : 4));                       // smem ring depth
+  static constexpr int kTileBytes = C * QW * 4;                        // one [C][16] operand tile (C * 64 B, multiple of 512)
+  static constexpr int kStageBytes = 4 * kTileBytes;                   // role x [hi C rows ; lo C rows]
+  static constexpr int kTmemCols = 512;
+  static constexpr size_t kSmem = 1024 + 2 * (size_t)kGBytes + (size_t)kNB * kStageBytes + 1024;
   static_assert(C % 16 == 0 && C >= 16 && C <= 128, "N = C must be a multiple of 16 (M = 128) and fit TMEM");
-  static_assert(2 * C + kStages * kACols <= 512, "TMEM budget");
+  static_assert(kNS >= 3 && kNB >= kNS && 2 * kDCols + kNS * kACols <= 512, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
+__device__ __forceinline__ void conv_bar_sync() {      // named barrier over the converter warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+}
+
 template <int C>
-__global__ void __launch_bounds__(kTcThreads, C <= 32 ? 2 : 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const __grid_constant__ CUtensorMap f1map,
                           const __grid_constant__ CUtensorMap f2map, const float* __restrict__ gout, long long gout_bs,
                           float* __restrict__ gf1, float* __restrict__ gf2, int H, int W, float inv_c) {
   using Cfg = TcCfg<C>;
-  constexpr int S = Cfg::kStages;
+  constexpr int NS = Cfg::kNS, NB = Cfg::kNB;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned carve-up (the operand tiles need 512 for SWIZZLE_64B)
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* g1 = reinterpret_cast<float*>(base);                          // [81][128]  gout tile
   float* g2 = g1 + NDISP * TH * TW;                                    // [81][128]  sheared gout tile
-  unsigned char* ring = base + 2 * kGBytes;                            // [S][role][hi/lo][C][16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S * Cfg::kStageBytes);
-  uint64_t* bar_g = bars;                 // gout tiles landed
-  uint64_t* bar_bfull = bars + 1;         // [S] feature rows landed
-  uint64_t* bar_ready = bars + 1 + S;     // [S] converters done (A in TMEM, B_lo in smem)
-  uint64_t* bar_free = bars + 1 + 2 * S;  // [S] MMAs of the stage retired
-  uint64_t* bar_done = bars + 1 + 3 * S;  // all MMAs retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 3 * S);
+  unsigned char* ring = base + 2 * kGBytes;                            // [NB][role]{[C][16] raw feature row (TMA) ; [C][16] lo}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NB * Cfg::kStageBytes);
+  uint64_t* bar_g = bars;                      // gout tile landed
+  uint64_t* bar_bfull = bars + 1;              // [NB] feature rows landed
+  uint64_t* bar_bfree = bar_bfull + NB;        // [NB] MMAs that read the smem stage retired
+  uint64_t* bar_ready = bar_bfree + NB;        // [NS] converters done (A chunks in TMEM, B_lo in smem)
+  uint64_t* bar_free = bar_ready + NS;         // [NS] MMAs that read the TMEM stage retired
+  uint64_t* bar_done = bar_free + NS;          // all MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
@@ -86,8 +114,11 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
     tma_prefetch_desc(&f1map);
     tma_prefetch_desc(&f2map);
     mbar_init(bar_g, 1);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < NB; ++s) {
       mbar_init(bar_bfull + s, 1);
+      mbar_init(bar_bfree + s, 1);
+    }
+    for (int s = 0; s < NS; ++s) {
       mbar_init(bar_ready + s, 4);
       mbar_init(bar_free + s, 1);
     }
@@ -102,8 +133,8 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: [0,C) D_0 (gf1)   [C,2C) D_1 (gf2)   [2C + 64 s, +64): stage s = {A_0 hi, A_0 lo, A_1 hi, A_1 lo} x 16
-  const uint32_t tmem_a = tmem + 2 * C;
+  // TMEM columns: [0, kDCols) role 0 accumulators, [kDCols, 2 kDCols) role 1, then NS stages {A0 hi, A0 lo, A1 hi, A1 lo} x 16
+  const uint32_t tmem_a = tmem + 2 * Cfg::kDCols;
 
   if (warp == 0) {
     // ================================================= TMA producer =================================================
@@ -111,59 +142,69 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
       mbar_expect_tx(bar_g, kGBytes);
       tma_load_4d(g1, &gmap_tile, bar_g, x0, y0, 0, b);
       for (int c = 0; c < QH; ++c) {
-        const int s = c % S;
-        if (c >= S) mbar_wait(bar_free + s, ((c / S) - 1) & 1);
-        unsigned char* st = ring + s * Cfg::kStageBytes;
-        mbar_expect_tx(bar_bfull + s, 2 * Cfg::kTileBytes);
-        tma_load_4d(st, &f2map, bar_bfull + s, x0 - RAD, 0, y0 - RAD + c, b);                          // role 0: f2 row
-        tma_load_4d(st + 2 * Cfg::kTileBytes, &f1map, bar_bfull + s, x0 - RAD, 0, y0 - RAD + c, b);    // role 1: f1 row
+        const int sb = c % NB;
+        if (c >= NB) mbar_wait(bar_bfree + sb, ((c / NB) - 1) & 1);
+        unsigned char* st = ring + sb * Cfg::kStageBytes;
+        mbar_expect_tx(bar_bfull + sb, 2 * Cfg::kTileBytes);
+        // role 0 (gf1) contracts with f2, role 1 (gf2) with f1; same window row for both
+        tma_load_4d(st, &f2map, bar_bfull + sb, x0 - RAD, 0, y0 - RAD + c, b);
+        tma_load_4d(st + 2 * Cfg::kTileBytes, &f1map, bar_bfull + sb, x0 - RAD, 0, y0 - RAD + c, b);
       }
     }
   } else if (warp == 1) {
     // ================================================== MMA issuer ==================================================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_tf32(128, C);
+      constexpr uint32_t idesc_c = tc::idesc_tf32(128, C), idesc_2c = tc::idesc_tf32(128, Cfg::kStack ? 2 * C : C);
       for (int c = 0; c < QH; ++c) {
-        const int s = c % S;
-        const uint32_t par = (c / S) & 1;
-        mbar_wait(bar_bfull + s, par);
-        mbar_wait(bar_ready + s, par);
+        const int s = c % NS, sb = c % NB;
+        mbar_wait(bar_bfull + sb, (c / NB) & 1);
+        mbar_wait(bar_ready + s, (c / NS) & 1);
         tc::fence_after_sync();
-        const uint32_t st = smem_u32(ring + s * Cfg::kStageBytes);
+        const uint32_t st = smem_u32(ring + sb * Cfg::kStageBytes);
         const uint32_t ta = tmem_a + s * Cfg::kACols;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const uint32_t d = tmem + r * C;
+          const uint32_t hi = st + 2 * r * Cfg::kTileBytes, lo = hi + Cfg::kTileBytes;
+          const uint32_t d = tmem + r * Cfg::kDCols;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t bh = tc::smem_desc_kmajor(st + (2 * r) * Cfg::kTileBytes + 32 * ks, 512, tc::kLayoutSw64);
-            const uint64_t bl = tc::smem_desc_kmajor(st + (2 * r + 1) * Cfg::kTileBytes + 32 * ks, 512, tc::kLayoutSw64);
+            const uint64_t bh = tc::smem_desc_kmajor(hi + 32 * ks, 512, tc::kLayoutSw64);
             const uint32_t ah = ta + 32 * r + 8 * ks, al = ah + 16;
-            tc::mma_tf32_ts(d, ah, bh, idesc, c > 0 || ks > 0);      // hi * hi
-            tc::mma_tf32_ts(d, al, bh, idesc, true);                 // lo * hi
-            tc::mma_tf32_ts(d, ah, bl, idesc, true);                 // hi * lo
+            const bool acc = c > 0 || ks > 0;
+            if (Cfg::kStack) {
+              tc::mma_tf32_ts(d, ah, bh, idesc_2c, acc);             // A_hi * [B_hi ; B_lo]  -> columns [0, 2C)
+              tc::mma_tf32_ts(d, al, bh, idesc_c, true);             // A_lo * B_hi           -> columns [0, C)
+            } else {
+              const uint64_t bl = tc::smem_desc_kmajor(lo + 32 * ks, 512, tc::kLayoutSw64);
+              tc::mma_tf32_ts(d, ah, bh, idesc_c, acc);              // hi * hi
+              tc::mma_tf32_ts(d, al, bh, idesc_c, true);             // lo * hi
+              tc::mma_tf32_ts(d, ah, bl, idesc_c, true);             // hi * lo
+            }
           }
         }
-        tc::mma_commit(bar_free + s);      // stage reusable when these MMAs have read their operands
+        tc::mma_commit(bar_free + s);      // both stages (TMEM chunks, smem tiles) are released when these MMAs retire
+        tc::mma_commit(bar_bfree + sb);
       }
       tc::mma_commit(bar_done);
     }
   } else {
-    // ========================================= converters (4 warps) + epilogue =========================================
+    // ========================================= converters (3 x 4 warps) + epilogue =========================================
+    const int cw = warp - 2;                       // converter warp 0..11
+    const int grp = cw >> 2;                       // group 0..2
     const int q = warp & 3;                        // TMEM lane quadrant this warp may touch
     const int m = q * 32 + lane;                   // tile pixel = TMEM lane
     const int ty = m >> 3, tx = m & 7;
-    const int ty_lo = q * 4, ty_hi = q * 4 + 3;    // rows of this warp
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int ct = threadIdx.x - 64;               // 0..127: converter thread index for the B pass
+    const int gt = (cw & 3) * 32 + lane;           // 0..127: thread index inside the group (B pass)
     {
-      // sheared gout column of this lane: g2[d][m] = gout[b, d, y - (i-4), x - (j-4)], zero outside the image.  Thread-private
-      // (lane m only ever reads column m), so the copies need no barrier, just this thread's own cp.async wait.
+      // sheared gout tile g2[d][m] = gout[b, d, y - (i-4), x - (j-4)] (zero outside the image), displacement rows split over the
+      // groups: zero-filling 4-byte cp.async (the TMA unit rejects box origins that are not 16-byte aligned)
       const int y = y0 + ty, x = x0 + tx;
       const float* gb = gout + (size_t)b * gout_bs;
       const size_t plane = (size_t)H * W;
 #pragma unroll
-      for (int i = 0; i < ND; ++i) {
+      for (int ii = 0; ii < ND / kGroups; ++ii) {
+        const int i = ii * kGroups + grp;
         const int yy = y - (i - RAD);
         const bool yok = yy >= 0 && yy < H;
 #pragma unroll
@@ -177,58 +218,65 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
       cp_async_commit();
       cp_async_wait<0>();
     }
+    conv_bar_sync();                               // every group reads all of g2
     mbar_wait(bar_g, 0);
-    for (int c = 0; c < QH; ++c) {
-      const int s = c % S;
-      if (c >= S) {
-        mbar_wait(bar_free + s, ((c / S) - 1) & 1);
+    const uint32_t xmask = 0x1FFu << tx;           // window columns qx with 0 <= qx - tx <= 8
+    for (int c = grp; c < QH; c += kGroups) {
+      const int s = c % NS, sb = c % NB;
+      if (c >= NS) {
+        mbar_wait(bar_free + s, ((c / NS) - 1) & 1);
         tc::fence_after_sync();
       }
-      // ---- A chunks of window row qy = c -> TMEM
+      // ---- band chunks of window row qy = c, both roles -> TMEM
       const uint32_t ta = tmem_a + s * Cfg::kACols + lane_addr;
-      uint32_t h0[16], l0[16], h1[16], l1[16];
-      if (c >= ty_lo && c <= ty_hi + 2 * RAD) {    // warp-uniform: some lane of the warp is inside the band
-        const int dyi = c - ty;
-        const bool band_y = dyi >= 0 && dyi <= 2 * RAD;
+      const int dyi = c - ty;
+      const uint32_t msk = (dyi >= 0 && dyi <= 2 * RAD) ? xmask : 0u;
+      if (__any_sync(kFullMask, msk != 0u)) {
         const int d_base = dyi * ND - tx;          // d1 = d_base + qx
-        const float* p0 = g1 + d_base * (TH * TW) + m;
-        const float* p1 = g2 + (NDISP - 1 - d_base) * (TH * TW) + m;
+        const float* p0 = g1 + d_base * (TH * TW) + m;                       // role 0: g1[d1][m]
+        const float* p1 = g2 + (NDISP - 1 - d_base) * (TH * TW) + m;         // role 1: g2[80 - d1][m]
+        uint32_t h[16], l[16];
 #pragma unroll
         for (int qx = 0; qx < QW; ++qx) {
-          const bool in = band_y && qx >= tx && qx <= tx + 2 * RAD;
-          const float v0 = in ? p0[qx * (TH * TW)] : 0.0f;
-          const float v1 = in ? p1[-qx * (TH * TW)] : 0.0f;
-          h0[qx] = tc::tf32_hi(v0);
-          l0[qx] = tc::tf32_lo(v0, h0[qx]);
-          h1[qx] = tc::tf32_hi(v1);
-          l1[qx] = tc::tf32_lo(v1, h1[qx]);
+          const float v = ((msk >> qx) & 1u) ? p0[qx * (TH * TW)] : 0.0f;
+          h[qx] = tc::tf32_hi(v);
+          l[qx] = tc::tf32_lo(v, h[qx]);
         }
-      } else {
+        tc::tmem_st16(ta, h);
+        tc::tmem_st16(ta + 16, l);
 #pragma unroll
-        for (int qx = 0; qx < QW; ++qx) h0[qx] = l0[qx] = h1[qx] = l1[qx] = 0u;
+        for (int qx = 0; qx < QW; ++qx) {
+          const float v = ((msk >> qx) & 1u) ? p1[-qx * (TH * TW)] : 0.0f;
+          h[qx] = tc::tf32_hi(v);
+          l[qx] = tc::tf32_lo(v, h[qx]);
+        }
+        tc::tmem_st16(ta + 32, h);
+        tc::tmem_st16(ta + 48, l);
+      } else {
+        uint32_t z[16];
+#pragma unroll
+        for (int qx = 0; qx < QW; ++qx) z[qx] = 0u;
+        tc::tmem_st16(ta, z);
+        tc::tmem_st16(ta + 16, z);
+        tc::tmem_st16(ta + 32, z);
+        tc::tmem_st16(ta + 48, z);
       }
-      tc::tmem_st16(ta, h0);
-      tc::tmem_st16(ta + 16, l0);
-      tc::tmem_st16(ta + 32, h1);
-      tc::tmem_st16(ta + 48, l1);
-      // ---- B_lo = B - trunc_tf32(B) for both feature rows (same swizzled position in the lo buffer)
-      mbar_wait(bar_bfull + s, (c / S) & 1);
+      // ---- B_lo = B - trunc_tf32(B) for both feature rows (same swizzled position in the lo half)
+      mbar_wait(bar_bfull + sb, (c / NB) & 1);
       {
-        float4* st = reinterpret_cast<float4*>(ring + s * Cfg::kStageBytes);
+        float4* st = reinterpret_cast<float4*>(ring + sb * Cfg::kStageBytes);
         constexpr int kVec = Cfg::kTileBytes / 16;                     // float4 per tile = 4 C
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const float4* src = st + (2 * r) * kVec;
-          float4* dst = st + (2 * r + 1) * kVec;
 #pragma unroll
-          for (int i = ct; i < kVec; i += 128) {
-            const float4 v = src[i];
+          for (int i = gt; i < kVec; i += 128) {
+            const float4 v = st[2 * r * kVec + i];
             float4 o;
             o.x = __uint_as_float(tc::tf32_lo(v.x, tc::tf32_hi(v.x)));
             o.y = __uint_as_float(tc::tf32_lo(v.y, tc::tf32_hi(v.y)));
             o.z = __uint_as_float(tc::tf32_lo(v.z, tc::tf32_hi(v.z)));
             o.w = __uint_as_float(tc::tf32_lo(v.w, tc::tf32_hi(v.w)));
-            dst[i] = o;
+            st[(2 * r + 1) * kVec + i] = o;
           }
         }
       }
@@ -238,23 +286,30 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + s);
     }
-    // ---- epilogue: D_r[pixel][channel] -> g{f1,f2}[b][channel][y][x] * (1/C)
+    // ---- epilogue: D_r[pixel][channel] -> g{f1,f2}[b][channel][y][x] * (1/C); 16-channel chunks dealt round robin to the groups
     mbar_wait(bar_done, 0);
     tc::fence_after_sync();
     const int y = y0 + ty, x = x0 + tx;
     const bool live = y < H && x < W;
     const size_t plane = (size_t)H * W;
+    constexpr int kChunks = 2 * (C / 16);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float* dst = (r == 0 ? gf1 : gf2) + (size_t)b * C * plane + (size_t)y * W + x;
-#pragma unroll
-      for (int j = 0; j < C / 16; ++j) {
-        uint32_t v[16];
-        tc::tmem_ld16(tmem + lane_addr + r * C + 16 * j, v);
+    for (int e = 0; e < (kChunks + kGroups - 1) / kGroups; ++e) {
+      const int id = e * kGroups + grp;
+      if (id < kChunks) {
+        const int r = id / (C / 16), j = id - r * (C / 16);
+        float* dst = (r == 0 ? gf1 : gf2) + (size_t)b * C * plane + (size_t)y * W + x;
+        uint32_t v[16], w[16];
+        tc::tmem_ld16(tmem + lane_addr + r * Cfg::kDCols + 16 * j, v);
+        if (Cfg::kStack) tc::tmem_ld16(tmem + lane_addr + r * Cfg::kDCols + C + 16 * j, w);      // the A_hi * B_lo half
         tc::wait_ld();
         if (live) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) dst[(size_t)(16 * j + k) * plane] = __uint_as_float(v[k]) * inv_c;
+          for (int k = 0; k < 16; ++k) {
+            float acc = __uint_as_float(v[k]);
+            if (Cfg::kStack) acc += __uint_as_float(w[k]);
+            dst[(size_t)(16 * j + k) * plane] = acc * inv_c;
+          }
         }
       }
     }
