@@ -49,6 +49,30 @@ def test_cost_volume_vs_oracle(U, shape):
     assert_close(g2, r2, REL_TOL, 'corr grad f2')
 
 
+@pytest.mark.parametrize('shape', [(2, 32, 64, 208), (2, 64, 32, 104), (2, 96, 16, 52), (2, 128, 16, 24), (3, 64, 40, 72), (1, 32, 17, 12)])
+def test_cost_volume_tcgen05_backward(U, shape, monkeypatch):
+    """The tensor-core backward (csrc/cost_volume_tc.cu: banded 3xTF32 GEMM, tcgen05.mma with the band matrix in TMEM) is
+    opt-in -- it is not faster than the CUDA-core kernel (profiles/r2_tc_cost_volume_bwd.md) -- but it must stay parity
+    green: both gradients against the oracle at the pyramid-level shapes, a non-multiple-of-the-tile shape and image edges."""
+    monkeypatch.setenv('UOF_CV_FORCE_TC', '1')
+    g = torch.Generator().manual_seed(sum(shape))
+    B, C, H, W = shape
+    f1 = torch.randn(shape, generator=g).cuda().requires_grad_(True)
+    f2 = torch.randn(shape, generator=g).cuda().requires_grad_(True)
+    ct = torch.randn(B, 81, H, W, generator=g).cuda()
+    r1, r2 = torch.autograd.grad((O.cost_volume(f1, f2) * ct).sum(), (f1, f2))
+    from unopticalflow_b200 import _lib
+    n0 = _lib.launch_count()
+    g1, g2 = torch.autograd.grad((U.corr(f1, f2) * ct).sum(), (f1, f2))
+    assert _lib.launch_count() - n0 == 2          # forward + ONE backward launch (no fallback pair)
+    assert_close(g1, r1, 1e-5, 'tcgen05 corr grad f1')
+    assert_close(g2, r2, 1e-5, 'tcgen05 corr grad f2')
+    monkeypatch.delenv('UOF_CV_FORCE_TC')
+    h1, h2 = torch.autograd.grad((U.corr(f1, f2) * ct).sum(), (f1, f2))
+    assert_close(g1, h1, 1e-5, 'tcgen05 vs CUDA-core kernel')
+    assert_close(g2, h2, 1e-5, 'tcgen05 vs CUDA-core kernel')
+
+
 def test_cost_volume_golden(U):
     for tag in ('small', 'odd'):
         g = load_golden('corr_%s.npz' % tag)

@@ -8,9 +8,7 @@ import unopticalflow_b200 as U
 def run(shape, mode):
     for k in ('UOF_CV_NO_TC', 'UOF_CV_FORCE_TC'):
         os.environ.pop(k, None)
-    if mode == 'cuda':
-        os.environ['UOF_CV_NO_TC'] = '1'
-    else:
+    if mode != 'cuda':
         os.environ['UOF_CV_FORCE_TC'] = '1'
     B, C, H, W = shape
     g = torch.Generator(device='cuda').manual_seed(sum(shape))
@@ -31,7 +29,8 @@ def timeit(shape, mode, reps=20):
         sets.append((f1, f2, ct, U.corr(f1, f2)))
     for k in ('UOF_CV_NO_TC', 'UOF_CV_FORCE_TC'):
         os.environ.pop(k, None)
-    os.environ['UOF_CV_NO_TC' if mode == 'cuda' else 'UOF_CV_FORCE_TC'] = '1'
+    if mode != 'cuda':
+        os.environ['UOF_CV_FORCE_TC'] = '1'
     def go(i):
         f1, f2, ct, out = sets[i % nset]
         torch.autograd.grad(out, (f1, f2), ct, retain_graph=True)

@@ -1,33 +1,28 @@
-// a1 backward on the 5th-generation tensor cores: cost-volume gradient as a banded 3xTF32 GEMM (tcgen05 + TMEM + TMA).
+// a1 backward on the 5th-generation tensor cores: cost-volume gradient as a banded 3xTF32 GEMM (tcgen05 + TMEM).
+// OPT-IN (UOF_CV_TC=1): parity-green but NOT faster than the CUDA-core kernel (0.6-0.8x at C = 32, 1.0-1.2x at C = 64/96) --
+// measurements, pipeline trace and the reasons are in profiles/r2_tc_cost_volume_bwd.md; the default path stays
+// cost_volume_tma.cu.  Kept because it is the evidence behind "0.6 of the HBM roofline is unreachable for a1-bwd".
 // Reference math: PWC_tf.corr_naive, /root/reference/core/networks/structures/pwc_tf.py:97-106
 //   out[b, 9i+j, y, x] = (1/C) sum_c f1[b,c,y,x] * f2[b,c,y+i-4,x+j-4]
 //   gf1[c,p] = (1/C) sum_d gout[d,p]        * f2[c,p+disp(d)]            ("role 0")
 //   gf2[c,q] = (1/C) sum_d gout[d,q-disp(d)] * f1[c,q-disp(d)]            ("role 1"),   disp(9i+j) = (i-4, j-4)
-//
-// Why tensor cores: on CUDA cores this contraction is shared-memory-bandwidth bound at 0.26 of the HBM roofline / 0.30 of the
-// FP32 peak and needs 70-87 % of that peak to reach 0.6.
 //
 // Formulation.  A CTA owns a 16x8 pixel tile (M = 128 = the TMEM lanes) and all C channels (N = C).  The neighbourhood of
 // the tile is a 24x16 window (K = 384, index k = qy*16 + qx).  For both roles
 //   D_r[pixel m, channel c] = sum_k A_r[m, k] * F_r[c, window pixel k]
 // where F_0 = f2, F_1 = f1 over the SAME window and A_r is the band matrix of the gradient:
 //   lane m = (ty,tx), column k = (qy,qx) is non-zero iff 0 <= qy-ty <= 8 and 0 <= qx-tx <= 8; with d1 = 9(qy-ty) + (qx-tx)
-//   A_0[m,k] = gout[d1, tile pixel m]                                    (tile of gout, one TMA box load)
-//   A_1[m,k] = gout[80-d1, tile pixel m - disp(80-d1)] =: g2[80-d1][m]   (the "sheared" tile: every lane copies the 81
-//              values of ITS OWN column with zero-filling 4-byte cp.async -- the TMA unit rejects box origins that are not
-//              16-byte aligned (measured, tools/tc_probe.cu: illegal instruction), so a per-plane shifted box is not an option)
-// A_r lives in TENSOR MEMORY: the four converter warps build it one window row (16 columns) at a time from shared memory
+//   A_0[m,k] = gout[d1, tile pixel m]                                    (g1: the tile of gout)
+//   A_1[m,k] = gout[80-d1, tile pixel m - disp(80-d1)] =: g2[80-d1][m]   (g2: the "sheared" tile, gathered with zero-filling
+//              4-byte cp.async: the TMA unit rejects box origins that are not 16-byte aligned, tools/tc_probe.cu)
+// A_r lives in TENSOR MEMORY: converter warps build it one window row (16 columns) at a time from shared memory
 // (bank-conflict free: the address is (const - lane terms)*128 + lane) and write it with tcgen05.st, so the band matrix
-// never touches shared memory (in shared memory its construction + the tensor core's re-read would cost 7.5k cycles per
-// tile at 128 B/clk -- more than the CUDA-core kernel).  B = F_r arrives by TMA straight from the NCHW tensors through a
-// tensor map with permuted dimensions (x, c, y, b) and CU_TENSOR_MAP_SWIZZLE_64B: the box {16 x, C channels, 1 row} lands
-// as the K-major canonical UMMA layout ([channel][16 floats], 64-byte rows), out-of-image elements zero-filled.
-// fp32 parity (1e-4) needs 3xTF32: the tensor core TRUNCATES fp32 inputs to tf32 (measured, tools/tc_probe.cu), so
-// hi = x & 0xFFFFE000 is what it sees of the raw tile, lo = x - hi is computed by the converter warps (A: in registers on the
-// way to TMEM; B: one pass over the tile into a second buffer), and D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
-// 24 window rows x 2 roles x 2 K-steps x 3 = 288 tcgen05.mma (M=128, N=C, K=8) per tile, accumulators in TMEM, one elected
-// thread issues; a 3-4 stage mbarrier ring couples TMA producer -> converters -> MMA issuer -> (tcgen05.commit) -> back.
-// Epilogue: tcgen05.ld of D_0 / D_1, scale by 1/C, 32-byte-segment coalesced stores to gf1 / gf2.
+// never touches shared memory.  B = F_r is staged in shared memory in the K-major SWIZZLE_64B canonical UMMA layout
+// ([channel][16 floats], 64-byte rows).  fp32 parity (1e-4) needs 3xTF32: the tensor core TRUNCATES fp32 inputs to tf32
+// (measured), so hi = x & 0xFFFFE000 is what it sees of the raw tile, lo = x - hi is computed by the converter warps (A: in
+// registers on the way to TMEM; B: one pass over the tile), and D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+// One elected thread issues the tcgen05.mma's (M = 128, K = 8); mbarrier rings couple loader -> converters -> MMA issuer ->
+// (tcgen05.commit) -> back.  Epilogue: tcgen05.ld of the accumulators, scale by 1/C, 32-byte-segment stores to gf1 / gf2.
 #include <stdlib.h>
 
 #include "cost_volume.h"
@@ -86,9 +81,18 @@ __device__ __forceinline__ void conv_bar_sync() {      // named barrier over the
 
 template <int C>
 __global__ void __launch_bounds__(kTcThreads, 1)
-cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const __grid_constant__ CUtensorMap f1map,
-                          const __grid_constant__ CUtensorMap f2map, const float* __restrict__ gout, long long gout_bs,
-                          float* __restrict__ gf1, float* __restrict__ gf2, int H, int W, float inv_c) {
+cost_volume_bwd_tc_kernel(const float* __restrict__ gout, long long gout_bs, const float* __restrict__ f1,
+                          const float* __restrict__ f2, float* __restrict__ gf1, float* __restrict__ gf2, int H, int W,
+                          float inv_c, long long* __restrict__ trace) {
+  // trace != nullptr (UOF_CV_TC_TRACE, tools/cv_tc_trace.py): CTA (0,0,0) records clock64() at every pipeline event of every
+  // window row -- [row][event]: 0 loader issued, 1 loader published, 2 converter got its TMEM stage, 3 band chunks stored,
+  // 4 feature row seen, 5 ready signalled, 6 MMA issuer got the row, 7 MMAs issued + committed; rows 24.. hold
+  // {prologue done, accumulators complete, epilogue done}.
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define UOF_TRACE(row, ev)                                   \
+  do {                                                       \
+    if (tr) trace[(row) * 8 + (ev)] = clock64();             \
+  } while (0)
   using Cfg = TcCfg<C>;
   constexpr int NS = Cfg::kNS, NB = Cfg::kNB;
   extern __shared__ unsigned char smem_raw[];
@@ -98,7 +102,6 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
   float* g2 = g1 + NDISP * TH * TW;                                    // [81][128]  sheared gout tile
   unsigned char* ring = base + 2 * kGBytes;                            // [NB][role]{[C][16] raw feature row (TMA) ; [C][16] lo}
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NB * Cfg::kStageBytes);
-  uint64_t* bar_g = bars;                      // gout tile landed
   uint64_t* bar_bfull = bars + 1;              // [NB] feature rows landed
   uint64_t* bar_bfree = bar_bfull + NB;        // [NB] MMAs that read the smem stage retired
   uint64_t* bar_ready = bar_bfree + NB;        // [NS] converters done (A chunks in TMEM, B_lo in smem)
@@ -110,10 +113,6 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&gmap_tile);
-    tma_prefetch_desc(&f1map);
-    tma_prefetch_desc(&f2map);
-    mbar_init(bar_g, 1);
     for (int s = 0; s < NB; ++s) {
       mbar_init(bar_bfull + s, 1);
       mbar_init(bar_bfree + s, 1);
@@ -137,18 +136,47 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
   const uint32_t tmem_a = tmem + 2 * Cfg::kDCols;
 
   if (warp == 0) {
-    // ================================================= TMA producer =================================================
-    if (lane == 0) {
-      mbar_expect_tx(bar_g, kGBytes);
-      tma_load_4d(g1, &gmap_tile, bar_g, x0, y0, 0, b);
-      for (int c = 0; c < QH; ++c) {
+    // ============================================ feature-row loader (one warp) ============================================
+    // 16-byte zero-filling cp.async into the K-major SWIZZLE_64B canonical layout: row = channel (64 bytes = the 16 window
+    // columns), the 16-byte chunk index XORed with (channel >> 1) & 3.  W % 4 == 0 and x0 % 8 == 0, so a chunk is entirely
+    // inside or entirely outside the image.  NOT the TMA unit: a {16 x, C channels, 1 row} box is C box rows of 64 bytes one
+    // channel plane apart, and the TMA engine needed ~25 cycles per such row -- 1536 rows = 38k cycles per tile, which made
+    // v1-v6 of this kernel slower than the CUDA-core one whatever else was tuned (profiles/r2_tc_bwd_*).
+    constexpr int kLag = 3;                       // rows in flight per lane before the oldest is published
+    static_assert(NB > kLag, "ring too shallow for the loader lag");
+    constexpr int kChunks = C * 4;                // 16-byte chunks per [C][16] tile
+    const size_t plane = (size_t)H * W;
+    const float* src1 = f1 + (size_t)b * C * plane;
+    const float* src2 = f2 + (size_t)b * C * plane;
+    for (int c = 0; c < QH + kLag; ++c) {
+      if (c < QH) {
         const int sb = c % NB;
         if (c >= NB) mbar_wait(bar_bfree + sb, ((c / NB) - 1) & 1);
+        const int yy = y0 - RAD + c;
+        const bool rowok = yy >= 0 && yy < H;
         unsigned char* st = ring + sb * Cfg::kStageBytes;
-        mbar_expect_tx(bar_bfull + sb, 2 * Cfg::kTileBytes);
-        // role 0 (gf1) contracts with f2, role 1 (gf2) with f1; same window row for both
-        tma_load_4d(st, &f2map, bar_bfull + sb, x0 - RAD, 0, y0 - RAD + c, b);
-        tma_load_4d(st + 2 * Cfg::kTileBytes, &f1map, bar_bfull + sb, x0 - RAD, 0, y0 - RAD + c, b);
+#pragma unroll
+        for (int i = 0; i < kChunks / 32; ++i) {
+          const int k = lane + 32 * i, ch = k >> 2, part = k & 3;
+          const int xx = x0 - RAD + 4 * part;
+          const bool ok = rowok && xx >= 0 && xx < W;
+          const size_t off = (size_t)ch * plane + (size_t)(rowok ? yy : 0) * W + (ok ? xx : 0);
+          float* dst = reinterpret_cast<float*>(st + ch * 64 + ((part ^ ((ch >> 1) & 3)) << 4));
+          // role 0 (gf1) contracts with f2, role 1 (gf2) with f1; same window row for both
+          cp_async_16(dst, src2 + off, ok);
+          cp_async_16(dst + 2 * Cfg::kTileBytes / 4, src1 + off, ok);
+        }
+      }
+      cp_async_commit();
+      if (lane == 0 && c < QH) UOF_TRACE(c, 0);
+      if (c >= kLag) {
+        cp_async_wait<kLag>();
+        tc::fence_proxy_async();                  // the tensor core reads these tiles through the async proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_bfull + (c - kLag) % NB);
+          UOF_TRACE(c - kLag, 1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -160,6 +188,7 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
         mbar_wait(bar_bfull + sb, (c / NB) & 1);
         mbar_wait(bar_ready + s, (c / NS) & 1);
         tc::fence_after_sync();
+        UOF_TRACE(c, 6);
         const uint32_t st = smem_u32(ring + sb * Cfg::kStageBytes);
         const uint32_t ta = tmem_a + s * Cfg::kACols;
 #pragma unroll
@@ -184,6 +213,7 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
         }
         tc::mma_commit(bar_free + s);      // both stages (TMEM chunks, smem tiles) are released when these MMAs retire
         tc::mma_commit(bar_bfree + sb);
+        UOF_TRACE(c, 7);
       }
       tc::mma_commit(bar_done);
     }
@@ -215,11 +245,20 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
           cp_async_4(g2 + d * (TH * TW) + m, ok ? gb + d * plane + (size_t)yy * W + xx : gb, ok);
         }
       }
+      // straight gout tile g1[d][m] = gout[b, d, y0 + ty, x0 + tx]: 81 x 16 rows of two 16-byte chunks (x0 % 8 == 0, W % 4 == 0)
+      const int ctid = cw * 32 + lane;
+      for (int k = ctid; k < NDISP * TH * 2; k += kConvThreads) {
+        const int d = k >> 5, rem = k & 31, row = rem >> 1, half = rem & 1;
+        const int yy = y0 + row, xx = x0 + 4 * half;
+        const bool ok = yy < H && xx < W;
+        cp_async_16(g1 + d * (TH * TW) + row * TW + 4 * half, ok ? gb + d * plane + (size_t)yy * W + xx : gb, ok);
+      }
       cp_async_commit();
       cp_async_wait<0>();
     }
-    conv_bar_sync();                               // every group reads all of g2
-    mbar_wait(bar_g, 0);
+    conv_bar_sync();                               // every group reads all of g1 / g2
+    const bool trc = (cw & 3) == 0 && lane == 0;   // first warp of each group records
+    if (cw == 0 && lane == 0) UOF_TRACE(QH, 0);
     const uint32_t xmask = 0x1FFu << tx;           // window columns qx with 0 <= qx - tx <= 8
     for (int c = grp; c < QH; c += kGroups) {
       const int s = c % NS, sb = c % NB;
@@ -227,6 +266,7 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
         mbar_wait(bar_free + s, ((c / NS) - 1) & 1);
         tc::fence_after_sync();
       }
+      if (trc) UOF_TRACE(c, 2);
       // ---- band chunks of window row qy = c, both roles -> TMEM
       const uint32_t ta = tmem_a + s * Cfg::kACols + lane_addr;
       const int dyi = c - ty;
@@ -262,7 +302,9 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
         tc::tmem_st16(ta + 48, z);
       }
       // ---- B_lo = B - trunc_tf32(B) for both feature rows (same swizzled position in the lo half)
+      if (trc) UOF_TRACE(c, 3);
       mbar_wait(bar_bfull + sb, (c / NB) & 1);
+      if (trc) UOF_TRACE(c, 4);
       {
         float4* st = reinterpret_cast<float4*>(ring + sb * Cfg::kStageBytes);
         constexpr int kVec = Cfg::kTileBytes / 16;                     // float4 per tile = 4 C
@@ -285,10 +327,12 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + s);
+      if (trc) UOF_TRACE(c, 5);
     }
     // ---- epilogue: D_r[pixel][channel] -> g{f1,f2}[b][channel][y][x] * (1/C); 16-channel chunks dealt round robin to the groups
     mbar_wait(bar_done, 0);
     tc::fence_after_sync();
+    if (cw == 0 && lane == 0) UOF_TRACE(QH, 1);
     const int y = y0 + ty, x = x0 + tx;
     const bool live = y < H && x < W;
     const size_t plane = (size_t)H * W;
@@ -316,53 +360,57 @@ cost_volume_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap_tile, const _
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) UOF_TRACE(QH, 2);
+#undef UOF_TRACE
   if (warp == 1) tc::tmem_dealloc(tmem, Cfg::kTmemCols);
 }
 
+long long* g_trace = nullptr;      // device buffer for UOF_CV_TC_TRACE (debug only)
+
 template <int C>
-int launch_bwd_tc(const CUtensorMap& gt, const CUtensorMap& m1, const CUtensorMap& m2, const float* gout, long long gout_bs,
-                  float* gf1, float* gf2, int B, int H, int W, cudaStream_t stream) {
+int launch_bwd_tc(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int H,
+                  int W, cudaStream_t stream) {
   auto kern = cost_volume_bwd_tc_kernel<C>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmem));
-  kern<<<dim3(ceil_div(W, TW), ceil_div(H, TH), B), kTcThreads, TcCfg<C>::kSmem, stream>>>(gt, m1, m2, gout, gout_bs, gf1, gf2,
-                                                                                            H, W, 1.0f / (float)C);
+  kern<<<dim3(ceil_div(W, TW), ceil_div(H, TH), B), kTcThreads, TcCfg<C>::kSmem, stream>>>(gout, gout_bs, f1, f2, gf1, gf2, H, W,
+                                                                                            1.0f / (float)C, g_trace);
   count_launch();
   return check_launch("cost_volume_bwd (tcgen05)");
 }
 
 }  // namespace
 
-// Tensor-core backward.  Returns false when it does not apply (C not in {32,64,96,128}, W % 4 != 0, unaligned pointers,
-// small levels that do not fill the machine, UOF_CV_NO_TC=1, no driver entry point); otherwise launches and stores the status.
+// Debug: allocate (once) and return the device trace buffer of (QH + 1) x 8 clock64 stamps; see the kernel.
+extern "C" long long* uof_cv_tc_trace_buffer() {
+  if (!g_trace) {
+    if (cudaMalloc(&g_trace, (QH + 1) * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_trace, 0, (QH + 1) * 8 * sizeof(long long));
+  }
+  return g_trace;
+}
+
+extern "C" int uof_cv_tc_trace_read(long long* host) {
+  if (!g_trace) return 1;
+  return cudaMemcpy(host, g_trace, (QH + 1) * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+
+// Tensor-core backward, opt-in: UOF_CV_TC=1 uses it where a level fills the machine, UOF_CV_FORCE_TC=1 wherever the shape
+// allows.  Returns false when it is not selected or does not apply (C not in {32,64,96,128}, W % 4 != 0, unaligned pointers);
+// otherwise launches and stores the status.
 bool bwd_tc(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
             int H, int W, cudaStream_t stream, int* rc) {
-  const bool off = getenv("UOF_CV_NO_TC") != nullptr;          // read per call: tests and benches switch paths at run time
-  const bool force = getenv("UOF_CV_FORCE_TC") != nullptr;
-  if (off || !(C == 32 || C == 64 || C == 96 || C == 128)) return false;
+  const bool force = getenv("UOF_CV_FORCE_TC") != nullptr;     // read per call: tests and benches switch paths at run time
+  const bool on = force || getenv("UOF_CV_TC") != nullptr;
+  if (!on || !(C == 32 || C == 64 || C == 96 || C == 128)) return false;
   if (W % 4 != 0 || gout_bs % 4 != 0 || !aligned16(gout) || !aligned16(f1) || !aligned16(f2)) return false;
   if (B > 65535 || ceil_div(H, TH) > 65535) return false;
   const long long tiles = (long long)ceil_div(W, TW) * ceil_div(H, TH) * B;
   if (!force && tiles < 2 * kNumSMs) return false;          // the latency-bound small levels keep their own kernels
-  CUtensorMap gt, m1, m2;
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NDISP, (cuuint64_t)B};
-    const cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)gout_bs * 4};
-    const cuuint32_t box_tile[4] = {TW, TH, NDISP, 1};
-    if (!make_map_4d(&gt, gout, dims, str, box_tile, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
-  }
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t str[3] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4, (cuuint64_t)W * H * C * 4};
-    const cuuint32_t box[4] = {QW, (cuuint32_t)C, 1, 1};
-    if (!make_map_4d(&m1, f1, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
-        !make_map_4d(&m2, f2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))
-      return false;
-  }
   switch (C) {
-    case 32: *rc = launch_bwd_tc<32>(gt, m1, m2, gout, gout_bs, gf1, gf2, B, H, W, stream); break;
-    case 64: *rc = launch_bwd_tc<64>(gt, m1, m2, gout, gout_bs, gf1, gf2, B, H, W, stream); break;
-    case 96: *rc = launch_bwd_tc<96>(gt, m1, m2, gout, gout_bs, gf1, gf2, B, H, W, stream); break;
-    default: *rc = launch_bwd_tc<128>(gt, m1, m2, gout, gout_bs, gf1, gf2, B, H, W, stream); break;
+    case 32: *rc = launch_bwd_tc<32>(gout, gout_bs, f1, f2, gf1, gf2, B, H, W, stream); break;
+    case 64: *rc = launch_bwd_tc<64>(gout, gout_bs, f1, f2, gf1, gf2, B, H, W, stream); break;
+    case 96: *rc = launch_bwd_tc<96>(gout, gout_bs, f1, f2, gf1, gf2, B, H, W, stream); break;
+    default: *rc = launch_bwd_tc<128>(gout, gout_bs, f1, f2, gf1, gf2, B, H, W, stream); break;
   }
   return true;
 }
