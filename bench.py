@@ -136,6 +136,12 @@ def algorithmic_bytes(name, args):
     if name == 'uof_cost_volume_bwd':
         B, C, H, W = args[6:10]
         return (4 * C + 81) * 4 * B * H * W
+    if name == 'uof_cost_volume_fwd_ex':
+        B, C, H, W = (int(v) for v in args[4:8])
+        return (2 * C + 81) * 4 * B * H * W
+    if name == 'uof_cost_volume_bwd_ex':        # + the concat-slice gradient read by the epilogue, when given
+        B, C, H, W = (int(v) for v in args[9:13])
+        return (4 * C + 81 + (C if args[5] else 0)) * 4 * B * H * W
     if name == 'uof_warp_fwd':
         B, C, H, W = args[3:7]
         return (2 * C + 2) * 4 * B * H * W
@@ -167,6 +173,12 @@ def algorithmic_bytes(name, args):
     if name in ('uof_upsample_bilinear_fwd', 'uof_upsample_bilinear_bwd'):      # read one side, write the other
         planes, h, w, H, W = (int(v) for v in args[2:7])
         return 4 * planes * (h * w + H * W)
+    if name == 'uof_upsample_bilinear_fwd2':    # + the second destination
+        planes, h, w, H, W = (int(v) for v in args[5:10])
+        return 4 * planes * (h * w + (2 if args[2] else 1) * H * W)
+    if name == 'uof_upsample_bilinear_bwd3':    # + the extra gradient sources
+        planes, h, w, H, W = (int(v) for v in args[6:11])
+        return 4 * planes * (h * w + (1 + bool(args[1]) + bool(args[4])) * H * W)
     if name == 'uof_img_pyramid_stacked':      # read the triplet once, write level 0 and the coarser levels
         nimg, B, C, H, W = (int(v) for v in args[9:14])
         return int(4 * nimg * B * C * H * W * (2 + 0.25 + 0.0625))
@@ -186,7 +198,15 @@ class KernelObserver:
     @staticmethod
     def key_of(name, args):
         key = name
-        if name.startswith('uof_cost_volume') or name.startswith('uof_warp'):
+        if name == 'uof_cost_volume_fwd_ex':        # same kernels as the plain entry points: same key
+            key = 'uof_cost_volume_fwd[%s]' % 'x'.join(str(int(d)) for d in args[4:8])
+        elif name == 'uof_cost_volume_bwd_ex':
+            key = 'uof_cost_volume_bwd[%s]' % 'x'.join(str(int(d)) for d in args[9:13])
+        elif name == 'uof_upsample_bilinear_fwd2':
+            key = 'uof_upsample_bilinear_fwd[%s]' % 'x'.join(str(int(d)) for d in args[5:10])
+        elif name == 'uof_upsample_bilinear_bwd3':
+            key = 'uof_upsample_bilinear_bwd[%s]' % 'x'.join(str(int(d)) for d in args[6:11])
+        elif name.startswith('uof_cost_volume') or name.startswith('uof_warp'):
             dims = args[3:7] if name.endswith('fwd') else (args[6:10] if 'cost' in name else args[5:9])
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in dims))
             if name == 'uof_warp_bwd':

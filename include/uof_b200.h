@@ -51,6 +51,18 @@ int uof_cost_volume_bwd(const float* gout, long long gout_batch_stride,
                         const float* f1, const float* f2, float* gf1, float* gf2,
                         int B, int C, int H, int W, uof_stream_t stream);
 
+/* a1 + decoder glue (pwc_tf.py:119-131): the same cost volume with
+ *   - f1 read in place with an explicit batch stride (floats), e.g. the `c1` slice of the decoder's concat buffer
+ *     cat((corr, c1, up_flow), 1), so c1 is stored once;
+ *   - backward: `gadd` (nullable, (B,C,H,W) view with batch stride `gadd_batch_stride`) is added to gf1 in the kernel's
+ *     epilogue -- the gradient of that concat slice -- so d/d c1 needs no separate add. */
+int uof_cost_volume_fwd_ex(const float* f1, long long f1_batch_stride, const float* f2, float* out,
+                           int B, int C, int H, int W, long long out_batch_stride, uof_stream_t stream);
+int uof_cost_volume_bwd_ex(const float* gout, long long gout_batch_stride,
+                           const float* f1, long long f1_batch_stride, const float* f2,
+                           const float* gadd, long long gadd_batch_stride, float* gf1, float* gf2,
+                           int B, int C, int H, int W, uof_stream_t stream);
+
 /* a2/a3: bilinear backward warp.  Replaces warp_flow (net_utils.py:16-54): mesh grid,
  * normalisation, grid_sample(zeros padding) and, with use_mask, the validity mask
  * (sum of in-bounds corner weights >= 0.9999, net_utils.py:47-52) in ONE kernel.
@@ -196,6 +208,16 @@ int uof_upsample_bilinear_fwd(const float* in, float* out, int planes, int h, in
                               uof_stream_t stream);
 int uof_upsample_bilinear_bwd(const float* gout, float* gin, int planes, int h, int w, int H, int W, float scale,
                               uof_stream_t stream);
+
+/* Decoder glue (pwc_tf.py:119-125): the up-sampled flow has three consumers (warp, concat, residual add).
+ * fwd2: the values are also written to `out2` (nullable), a channel slice of a wider buffer: plane p goes to sample
+ * p / C2, channel p % C2, batch stride `out2_batch_stride` floats (the `up_flow` slice of the concat buffer).
+ * bwd3: the incoming gradient is gout + g2 + g3 (g2, g3 nullable): g2 addressed like out2 (the concat-slice gradient),
+ * g3 dense like gout (the residual branch); summed on the fly. */
+int uof_upsample_bilinear_fwd2(const float* in, float* out, float* out2, int C2, long long out2_batch_stride,
+                               int planes, int h, int w, int H, int W, float scale, uof_stream_t stream);
+int uof_upsample_bilinear_bwd3(const float* gout, const float* g2, int C2, long long g2_batch_stride, const float* g3,
+                               float* gin, int planes, int h, int w, int H, int W, float scale, uof_stream_t stream);
 
 /* a12: forward splat ("transformerFwd").  NOT in the reference.
  * u: (B,H,W,C) NHWC or NULL for a range map of ones (then C must be 1); flow: (B,H,W,2) in pixels;

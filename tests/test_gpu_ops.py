@@ -162,6 +162,82 @@ def test_conv_block_forked_activation(U, h, w):
     assert_close(gc, gd, 1e-5, 'forked conv block, single consumer')
 
 
+@pytest.mark.parametrize('shape', [(2, 8, 6, 9), (3, 17, 33, 70)] + LEVEL_SHAPES)
+def test_cost_volume_ex_strided_operand_and_folded_gradient(U, shape):
+    """uof_cost_volume_fwd_ex / _bwd_ex: f1 read in place from a channel slice of a wider buffer and the
+    slice's gradient added in the backward epilogue -- every kernel family (small, TMA, cp.async) against the oracle."""
+    import ctypes
+    from unopticalflow_b200 import _lib
+    g = torch.Generator().manual_seed(sum(shape) + 5)
+    B, C, H, W = shape
+    f1 = torch.randn(shape, generator=g, requires_grad=True)
+    f2 = torch.randn(shape, generator=g, requires_grad=True)
+    ct = torch.randn(B, 81 + C + 2, H, W, generator=g)
+    ref = O.cost_volume(f1, f2)
+    r1, r2 = torch.autograd.grad((ref * ct[:, :81]).sum() + (f1 * ct[:, 81:81 + C]).sum(), (f1, f2))
+    ctot, plane = 81 + C + 2, H * W
+    x = torch.full((B, ctot, H, W), float('nan'), device='cuda')
+    x[:, 81:81 + C] = f1.detach().cuda()
+    f2c, gx = f2.detach().cuda(), ct.cuda()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t, off=0: ctypes.c_void_p(t.data_ptr() + 4 * off)
+    _lib.call('uof_cost_volume_fwd_ex', P(x, 81 * plane), ctot * plane, P(f2c), P(x), B, C, H, W, ctot * plane, st)
+    assert_close(x[:, :81], ref, REL_TOL, 'corr fwd_ex')
+    assert torch.equal(x[:, 81:81 + C].cpu(), f1.detach())                    # the operand slice is untouched
+    g1, g2 = torch.empty_like(f2c), torch.empty_like(f2c)
+    _lib.call('uof_cost_volume_bwd_ex', P(gx), ctot * plane, P(x, 81 * plane), ctot * plane, P(f2c), P(gx, 81 * plane),
+              ctot * plane, P(g1), P(g2), B, C, H, W, st)
+    assert_close(g1, r1, REL_TOL, 'corr bwd_ex grad f1 (+ slice gradient)')
+    assert_close(g2, r2, REL_TOL, 'corr bwd_ex grad f2')
+
+
+def test_cost_volume_small_backward_opt_in():
+    """cost_volume_small.cu's backward kernel is opt-in (slower than the tiled kernels, see the note at bwd_small) but stays
+    parity green: re-run the cost-volume tests (every shape; the small ones take the kernel) in a subprocess with UOF_CV_SMALL_BWD=1."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, UOF_CV_SMALL_BWD='1')
+    sel = 'test_cost_volume_ex_strided_operand_and_folded_gradient or test_cost_volume_vs_oracle'
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', os.path.abspath(__file__), '-k',
+                        sel], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout
+
+
+@pytest.mark.parametrize('shape,rep', [((4, 32, 16, 24), 2), ((2, 128, 8, 26), 1), ((4, 96, 16, 52), 2), ((2, 64, 32, 104), 2),
+                                       ((2, 5, 6, 10), 1)])
+@pytest.mark.parametrize('ac', [False, True])
+def test_decoder_input_matches_reference_chain(U, shape, rep, ac):
+    """ops.decoder_input == pwc_tf.py:119-123 (interpolate x2 * 2 -> warp -> corr -> cat((corr, c1, up))) as the oracle
+    computes it: values of x and up, and every gradient (c with the replica sum, c2, the previous level's flow) with a
+    cotangent on BOTH outputs (up also feeds the residual add)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(sum(shape) + rep)
+    B, C, H, W = shape
+    c = torch.randn(B // rep, C, H, W, generator=g, requires_grad=True)
+    c2 = torch.randn(shape, generator=g, requires_grad=True)
+    fp = (torch.randn(B, 2, H // 2, W // 2, generator=g) * 1.5).requires_grad_(True)
+    ctx_, ctu = torch.randn(B, 81 + C + 2, H, W, generator=g), torch.randn(B, 2, H, W, generator=g)
+    up_r = F.interpolate(fp, scale_factor=2.0, mode='bilinear', align_corners=False) * 2.0
+    c1r = c.repeat(rep, 1, 1, 1)
+    x_r = torch.cat((O.cost_volume(c1r, O.warp_flow(c2, up_r, align_corners=ac)), c1r, up_r), 1)
+    rg = torch.autograd.grad((x_r * ctx_).sum() + (up_r * ctu).sum(), (c, c2, fp))
+    old = U.ops.COORD_ARITHMETIC
+    U.ops.COORD_ARITHMETIC = 'host'            # the CPU oracle's coordinate rounding
+    try:
+        a, b, f = gpu(c, True), gpu(c2, True), gpu(fp, True)
+        x, up = U.ops.decoder_input(a, b, f, ac)
+        gg = torch.autograd.grad((x * ctx_.cuda()).sum() + (up * ctu.cuda()).sum(), (a, b, f))
+    finally:
+        U.ops.COORD_ARITHMETIC = old
+    assert_close(up, up_r, 1e-6, 'decoder_input up')
+    assert torch.equal(x[:, 81 + C:], up) and torch.equal(x[:, 81:81 + C], a.detach().repeat(rep, 1, 1, 1))
+    assert_close(x, x_r, REL_TOL, 'decoder_input x')
+    for x_, y_, what in zip(gg, rg, ('c', 'c2', 'flow_prev')):
+        assert_close(x_, y_, REL_TOL, 'decoder_input grad ' + what)
+
+
 @pytest.mark.parametrize('shape', [(2, 32, 16, 24), (2, 5, 7, 9), (1, 64, 32, 104)])
 def test_corr_concat_matches_cat(U, shape):
     """Decoder glue fusion: cat((corr, c1, up), 1) with the cost volume written in place, values and grads."""

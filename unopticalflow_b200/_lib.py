@@ -42,6 +42,8 @@ _I, _LL, _P, _F = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_flo
 SIGNATURES = {
     'uof_cost_volume_fwd': [_P, _P, _P, _I, _I, _I, _I, _LL, _P],
     'uof_cost_volume_bwd': [_P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'uof_cost_volume_fwd_ex': [_P, _LL, _P, _P, _I, _I, _I, _I, _LL, _P],
+    'uof_cost_volume_bwd_ex': [_P, _LL, _P, _LL, _P, _P, _LL, _P, _P, _I, _I, _I, _I, _P],
     'uof_warp_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'uof_warp_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'uof_photo_loss_fwd': [ctypes.POINTER(PhotoLevel), _I, _I, _P, _P, _P, _P],
@@ -63,6 +65,8 @@ SIGNATURES = {
     'uof_bias_lrelu_bwd2': [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     'uof_upsample_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
     'uof_upsample_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
+    'uof_upsample_bilinear_fwd2': [_P, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _P],
+    'uof_upsample_bilinear_bwd3': [_P, _P, _I, _LL, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     'uof_img_pyramid': [_P, _LL, _LL, _LL, _LL, ctypes.POINTER(ctypes.c_void_p), _I, _I, _I, _I, _I, _I, _P],
     'uof_img_pyramid_stacked': [_P, _LL, _LL, _LL, _LL, _P, ctypes.POINTER(_I), ctypes.POINTER(ctypes.c_void_p), _I, _I, _I, _I, _I,
                                 _I, _P],

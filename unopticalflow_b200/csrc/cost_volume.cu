@@ -58,8 +58,8 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
 // ------------------------------------------------------------------------------------ forward
 template <bool VEC4>
 __global__ void __launch_bounds__(NT, 2)
-cost_volume_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
-                       int C, int H, int W, long long out_bs, int ksplit, float inv_c) {
+cost_volume_fwd_kernel(const float* __restrict__ f1, long long f1_bs, const float* __restrict__ f2,
+                       float* __restrict__ out, int C, int H, int W, long long out_bs, int ksplit, float inv_c) {
   extern __shared__ __align__(16) float smem[];
   constexpr int kStage = S1 + S2;      // stage k: f1 tile at smem + k*kStage, f2 halo tile S1 floats later
 
@@ -72,7 +72,7 @@ cost_volume_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f
   const int k_begin = ks * per, k_end = min(nchunks, k_begin + per);
   if (k_begin >= k_end) return;
 
-  const float* f1b = f1 + (size_t)b * C * H * W;
+  const float* f1b = f1 + (size_t)b * f1_bs;
   const float* f2b = f2 + (size_t)b * C * H * W;
 
   float acc[DYG][ND][PX];
@@ -153,9 +153,10 @@ cost_volume_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f
 // displacement-row groups are reduced through shared memory once per CK-channel chunk.
 template <bool VEC4>
 __global__ void __launch_bounds__(NT, 2)
-cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const float* __restrict__ f1,
-                       const float* __restrict__ f2, float* __restrict__ gf1, float* __restrict__ gf2,
-                       int C, int H, int W, int tiles_x, int csplit, float inv_c) {
+cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const float* __restrict__ f1, long long f1_bs,
+                       const float* __restrict__ f2, const float* __restrict__ gadd, long long gadd_bs,
+                       float* __restrict__ gf1, float* __restrict__ gf2, int C, int H, int W, int tiles_x, int csplit,
+                       float inv_c) {
   extern __shared__ __align__(16) float smem[];
   float* red = smem + 2 * S2;          // [NGROUP][CK][TH][TW]; halo stage k lives at smem + k*S2
 
@@ -169,9 +170,10 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
   const int k_begin = cs * per, k_end = min(nchunks, k_begin + per);
   if (k_begin >= k_end) return;
 
-  const float* src_b = (mirror ? f1 : f2) + (size_t)b * C * H * W;
+  const float* src_b = mirror ? f1 + (size_t)b * f1_bs : f2 + (size_t)b * C * H * W;
   float* dst_b = (mirror ? gf2 : gf1) + (size_t)b * C * H * W;
   const float* gb = gout + (size_t)b * gout_bs;
+  const float* add_b = (!mirror && gadd) ? gadd + (size_t)b * gadd_bs : nullptr;   // concat-slice gradient folded into gf1
   const size_t plane = (size_t)H * W;
   const int y = y0 + ty, x = x0 + PX * gx;
 
@@ -243,13 +245,19 @@ cost_volume_bwd_kernel(const float* __restrict__ gout, long long gout_bs, const 
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
       }
       float* o = dst_b + ((size_t)c * H + yy) * W + xx;
-      if (VEC4) {
-        *reinterpret_cast<float4*>(o) = make_float4(s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c);
-      } else {
-        const float v[4] = {s.x, s.y, s.z, s.w};
+      float v[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+      if (add_b) {
+        const float* ap = add_b + ((size_t)c * H + yy) * W + xx;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-          if (xx + p < W) o[p] = v[p] * inv_c;
+          if (xx + p < W) v[p] += __ldg(ap + p);
+      }
+      if (VEC4) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (xx + p < W) o[p] = v[p];
       }
     }
     // next iteration's first __syncthreads orders these reads of `red` before it is rewritten
@@ -271,15 +279,16 @@ bool vec4_ok(const void* a, const void* b, const void* c, int W, long long bs) {
 
 using namespace uof;
 
-extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W,
-                                   long long out_batch_stride, uof_stream_t stream_) {
+extern "C" int uof_cost_volume_fwd_ex(const float* f1, long long f1_batch_stride, const float* f2, float* out, int B, int C,
+                                      int H, int W, long long out_batch_stride, uof_stream_t stream_) {
   UOF_REQUIRE(f1 && f2 && out, "cost_volume_fwd: null pointer");
   UOF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cost_volume_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   UOF_REQUIRE(out_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_fwd: out_batch_stride too small");
+  UOF_REQUIRE(f1_batch_stride >= (long long)C * H * W, "cost_volume_fwd: f1_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = 0;
-  if (cv::fwd_small(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
-  if (cv::fwd_tma(f1, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
+  if (cv::fwd_small(f1, f1_batch_stride, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
+  if (cv::fwd_tma(f1, f1_batch_stride, f2, out, B, C, H, W, out_batch_stride, stream, &rc)) return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);
   const int ksplit = cv::pick_ksplit_atomic((long long)tx * ty * B, nchunks);
@@ -290,33 +299,51 @@ extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out,
   }
   dim3 grid(tx, ty, B * ksplit);
   const float inv_c = 1.0f / (float)C;
-  const bool v4 = vec4_ok(f1, f2, out, W, out_batch_stride);
+  const bool v4 = vec4_ok(f1, f2, out, W, out_batch_stride) && f1_batch_stride % 4 == 0;
   auto kern = v4 ? cost_volume_fwd_kernel<true> : cost_volume_fwd_kernel<false>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
-  kern<<<grid, NT, kFwdSmem, stream>>>(f1, f2, out, C, H, W, out_batch_stride, ksplit, inv_c);
+  kern<<<grid, NT, kFwdSmem, stream>>>(f1, f1_batch_stride, f2, out, C, H, W, out_batch_stride, ksplit, inv_c);
   count_launch();
   return check_launch("cost_volume_fwd");
 }
 
-extern "C" int uof_cost_volume_bwd(const float* gout, long long gout_batch_stride, const float* f1, const float* f2,
-                                   float* gf1, float* gf2, int B, int C, int H, int W, uof_stream_t stream_) {
+extern "C" int uof_cost_volume_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W,
+                                   long long out_batch_stride, uof_stream_t stream) {
+  return uof_cost_volume_fwd_ex(f1, (long long)C * H * W, f2, out, B, C, H, W, out_batch_stride, stream);
+}
+
+extern "C" int uof_cost_volume_bwd_ex(const float* gout, long long gout_batch_stride, const float* f1, long long f1_batch_stride,
+                                      const float* f2, const float* gadd, long long gadd_batch_stride, float* gf1, float* gf2,
+                                      int B, int C, int H, int W, uof_stream_t stream_) {
   UOF_REQUIRE(gout && f1 && f2 && gf1 && gf2, "cost_volume_bwd: null pointer");
   UOF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cost_volume_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   UOF_REQUIRE(gout_batch_stride >= (long long)UOF_NUM_DISPLACEMENTS * H * W, "cost_volume_bwd: gout_batch_stride too small");
+  UOF_REQUIRE(f1_batch_stride >= (long long)C * H * W, "cost_volume_bwd: f1_batch_stride too small");
+  UOF_REQUIRE(!gadd || gadd_batch_stride >= (long long)C * H * W, "cost_volume_bwd: gadd_batch_stride too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = 0;
-  if (cv::bwd_tc(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;      // tcgen05 banded GEMM
-  if (cv::bwd_tma(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;
+  const bool plain = f1_batch_stride == (long long)C * H * W && !gadd;
+  if (plain && cv::bwd_tc(gout, gout_batch_stride, f1, f2, gf1, gf2, B, C, H, W, stream, &rc)) return rc;      // tcgen05 banded GEMM (opt-in)
+  if (cv::bwd_small(gout, gout_batch_stride, f1, f1_batch_stride, f2, gadd, gadd_batch_stride, gf1, gf2, B, C, H, W, stream, &rc))
+    return rc;
+  if (cv::bwd_tma(gout, gout_batch_stride, f1, f1_batch_stride, f2, gadd, gadd_batch_stride, gf1, gf2, B, C, H, W, stream, &rc))
+    return rc;
   const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
   const int nchunks = ceil_div(C, CK);
   const int csplit = cv::pick_split((long long)tx * ty * B * 2, nchunks);
   UOF_REQUIRE((long long)B * csplit <= 65535, "cost_volume_bwd: batch too large for one launch");
   dim3 grid(tx * ty, 2, B * csplit);
   const float inv_c = 1.0f / (float)C;
-  const bool v4 = vec4_ok(f1, f2, gf1, W, gout_batch_stride) && vec4_ok(gf2, gout, gf1, W, 0);
+  const bool v4 = vec4_ok(f1, f2, gf1, W, gout_batch_stride) && vec4_ok(gf2, gout, gf1, W, f1_batch_stride);
   auto kern = v4 ? cost_volume_bwd_kernel<true> : cost_volume_bwd_kernel<false>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-  kern<<<grid, NT, kBwdSmem, stream>>>(gout, gout_batch_stride, f1, f2, gf1, gf2, C, H, W, tx, csplit, inv_c);
+  kern<<<grid, NT, kBwdSmem, stream>>>(gout, gout_batch_stride, f1, f1_batch_stride, f2, gadd, gadd_batch_stride, gf1, gf2, C, H, W,
+                                       tx, csplit, inv_c);
   count_launch();
   return check_launch("cost_volume_bwd");
+}
+
+extern "C" int uof_cost_volume_bwd(const float* gout, long long gout_batch_stride, const float* f1, const float* f2,
+                                   float* gf1, float* gf2, int B, int C, int H, int W, uof_stream_t stream) {
+  return uof_cost_volume_bwd_ex(gout, gout_batch_stride, f1, (long long)C * H * W, f2, nullptr, 0, gf1, gf2, B, C, H, W, stream);
 }

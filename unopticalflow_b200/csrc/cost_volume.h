@@ -45,15 +45,21 @@ inline int pick_ksplit_atomic(long long ctas, int nchunks) {
 
 // Smallest pyramid levels (<= 64 pixel quads per image): one CTA per (image, displacement row), no split-K atomics.
 // Returns false when the level is not small (or UOF_CV_NO_SMALL is set); otherwise launches and stores the status in *rc.
-bool fwd_small(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
+// `f1_bs`: batch stride of f1 in floats (C*H*W when dense; larger when f1 is the `c1` slice of the decoder's concat buffer).
+bool fwd_small(const float* f1, long long f1_bs, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
                cudaStream_t stream, int* rc);
 
 // TMA + mbarrier implementations.  Return false when the TMA path does not apply (W % 4 != 0, unaligned
 // pointers, no driver entry point, UOF_DISABLE_TMA=1); otherwise launch and store the status in *rc.
-bool fwd_tma(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
+// `gadd` (nullable, batch stride `gadd_bs`): a (B,C,H,W) view added to gf1 in the epilogue -- the gradient of the concat
+// buffer's `c1` slice, so that d/d c1 of cat((corr(c1, .), c1, .)) needs no separate add (pwc_tf.py:122-123).
+bool fwd_tma(const float* f1, long long f1_bs, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
              cudaStream_t stream, int* rc);
-bool bwd_tma(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
-             int H, int W, cudaStream_t stream, int* rc);
+bool bwd_tma(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
+             long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, cudaStream_t stream, int* rc);
+// Smallest levels (<= 64 pixel quads per image), cost_volume_small.cu.  Same contract.
+bool bwd_small(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
+               long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, cudaStream_t stream, int* rc);
 
 // Tensor-core (tcgen05 + TMEM) backward, cost_volume_tc.cu.  Same contract as bwd_tma.
 bool bwd_tc(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,

@@ -321,8 +321,9 @@ cost_volume_fwd_tma_persistent_kernel(const __grid_constant__ CUtensorMap map1, 
 template <class T>
 __global__ void __launch_bounds__(NT, 2)
 cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                           const float* __restrict__ gout, long long gout_bs, float* __restrict__ gf1,
-                           float* __restrict__ gf2, int C, int H, int W, int tiles_x, int csplit, float inv_c) {
+                           const float* __restrict__ gout, long long gout_bs, const float* __restrict__ gadd,
+                           long long gadd_bs, float* __restrict__ gf1, float* __restrict__ gf2, int C, int H, int W,
+                           int tiles_x, int csplit, float inv_c) {
   constexpr int TH = T::TH, TW = T::TW, HTH = T::HTH, HTW = T::HTW, S2 = T::S2, kRed = T::kRed;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* smem = align128(smem_raw);
@@ -363,6 +364,7 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 
   float* dst_b = (mirror ? gf2 : gf1) + (size_t)b * C * H * W;
   const float* gb = gout + (size_t)b * gout_bs;
+  const float* add_b = (!mirror && gadd) ? gadd + (size_t)b * gadd_bs : nullptr;   // concat-slice gradient folded into gf1
   const size_t plane = (size_t)H * W;
   const int y = y0 + ty, x = x0 + PX * gx;
 
@@ -433,8 +435,12 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
         const float4 t = *reinterpret_cast<const float4*>(rp + g * CK * TH * TW);
         sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
       }
-      *reinterpret_cast<float4*>(dst_b + ((size_t)c * H + yy) * W + xx) =
-          make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
+      float4 res = make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
+      if (add_b) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(add_b + ((size_t)c * H + yy) * W + xx));
+        res.x += a.x; res.y += a.y; res.z += a.z; res.w += a.w;
+      }
+      *reinterpret_cast<float4*>(dst_b + ((size_t)c * H + yy) * W + xx) = res;
     }
   }
 }
@@ -480,10 +486,10 @@ bool prefer_square(int H, int W, long long ctas_per_tile) {
 }
 
 template <class T>
-int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
+int launch_fwd(const float* f1, long long f1_bs, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
                cudaStream_t stream) {
   CUtensorMap m1, m2;
-  if (!make_nchw_map(&m1, f1, B, C, H, W, T::TW, T::TH, CK) || !make_nchw_map(&m2, f2, B, C, H, W, T::HTW, T::HTH, CK))
+  if (!make_nchw_map(&m1, f1, B, C, H, W, T::TW, T::TH, CK, f1_bs) || !make_nchw_map(&m2, f2, B, C, H, W, T::HTW, T::HTH, CK))
     return -1;
   const int tx = ceil_div(W, T::TW), ty = ceil_div(H, T::TH);
   int ksplit = pick_ksplit_atomic((long long)tx * ty * B, ceil_div(C, CK));
@@ -532,44 +538,46 @@ int launch_fwd(const float* f1, const float* f2, float* out, int B, int C, int H
 }
 
 template <class T>
-int launch_bwd(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
-               int H, int W, cudaStream_t stream) {
+int launch_bwd(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
+               long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, cudaStream_t stream) {
   CUtensorMap m1, m2;
-  if (!make_nchw_map(&m1, f1, B, C, H, W, T::HTW, T::HTH, CK) || !make_nchw_map(&m2, f2, B, C, H, W, T::HTW, T::HTH, CK))
+  if (!make_nchw_map(&m1, f1, B, C, H, W, T::HTW, T::HTH, CK, f1_bs) || !make_nchw_map(&m2, f2, B, C, H, W, T::HTW, T::HTH, CK))
     return -1;
   const int tx = ceil_div(W, T::TW), ty = ceil_div(H, T::TH);
   const int csplit = pick_split((long long)tx * ty * B * 2, ceil_div(C, CK));
   UOF_REQUIRE((long long)B * csplit <= 65535, "cost_volume_bwd: grid too large");
   auto kern = cost_volume_bwd_tma_kernel<T>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<T>()));
-  kern<<<dim3(tx * ty, 2, B * csplit), NT, bwd_smem<T>(), stream>>>(m1, m2, gout, gout_bs, gf1, gf2, C, H, W, tx, csplit,
-                                                                    1.0f / (float)C);
+  kern<<<dim3(tx * ty, 2, B * csplit), NT, bwd_smem<T>(), stream>>>(m1, m2, gout, gout_bs, gadd, gadd_bs, gf1, gf2, C, H, W,
+                                                                    tx, csplit, 1.0f / (float)C);
   count_launch();
   return check_launch("cost_volume_bwd (tma)");
 }
 
 }  // namespace
 
-bool fwd_tma(const float* f1, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
+bool fwd_tma(const float* f1, long long f1_bs, const float* f2, float* out, int B, int C, int H, int W, long long out_bs,
              cudaStream_t stream, int* rc) {
-  if (!tma_enabled() || W % 4 != 0 || out_bs % 4 != 0 || !aligned16(f1) || !aligned16(f2) || !aligned16(out)) return false;
-  const int r = prefer_square(H, W, B) ? launch_fwd<Tile<16, 16>>(f1, f2, out, B, C, H, W, out_bs, stream)
-                                       : launch_fwd<Tile<8, 32>>(f1, f2, out, B, C, H, W, out_bs, stream);
+  if (!tma_enabled() || W % 4 != 0 || out_bs % 4 != 0 || f1_bs % 4 != 0 || !aligned16(f1) || !aligned16(f2) || !aligned16(out))
+    return false;
+  const int r = prefer_square(H, W, B) ? launch_fwd<Tile<16, 16>>(f1, f1_bs, f2, out, B, C, H, W, out_bs, stream)
+                                       : launch_fwd<Tile<8, 32>>(f1, f1_bs, f2, out, B, C, H, W, out_bs, stream);
   if (r < 0) return false;    // tensor-map encoding unavailable: let the caller fall back
   *rc = r;
   return true;
 }
 
-bool bwd_tma(const float* gout, long long gout_bs, const float* f1, const float* f2, float* gf1, float* gf2, int B, int C,
-             int H, int W, cudaStream_t stream, int* rc) {
-  if (!tma_enabled() || W % 4 != 0 || gout_bs % 4 != 0 || !aligned16(f1) || !aligned16(f2) || !aligned16(gf1) ||
-      !aligned16(gf2) || !aligned16(gout))
+bool bwd_tma(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
+             long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, cudaStream_t stream, int* rc) {
+  if (!tma_enabled() || W % 4 != 0 || gout_bs % 4 != 0 || f1_bs % 4 != 0 || !aligned16(f1) || !aligned16(f2) ||
+      !aligned16(gf1) || !aligned16(gf2) || !aligned16(gout) || (gadd && (!aligned16(gadd) || gadd_bs % 4 != 0)))
     return false;
   // measured (profiles/): the backward kernel is faster with 8x32 tiles at every level of the 256x832 pyramid
   // (its reduction buffer and coefficient gathers favour wide rows); the square variant is kept behind UOF_CV_TILE=s
   const char* force = getenv("UOF_CV_TILE");
-  const int r = (force && force[0] == 's') ? launch_bwd<Tile<16, 16>>(gout, gout_bs, f1, f2, gf1, gf2, B, C, H, W, stream)
-                                           : launch_bwd<Tile<8, 32>>(gout, gout_bs, f1, f2, gf1, gf2, B, C, H, W, stream);
+  const int r = (force && force[0] == 's')
+                    ? launch_bwd<Tile<16, 16>>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, stream)
+                    : launch_bwd<Tile<8, 32>>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, stream);
   if (r < 0) return false;
   *rc = r;
   return true;

@@ -540,6 +540,7 @@ constexpr int kConsisFwdWarps = 4;   // forward: the warps of a block share one 
 template <int VEC>
 __global__ void __launch_bounds__(kConsisFwdWarps * 32)
 consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ sums) {
+  pdl_trigger();      // let the finalize grid (a programmatic dependent) be scheduled behind this grid's last wave
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kConsisFwdWarps + (threadIdx.x >> 5);
   int level = 0, b = 0, px0 = 0;
@@ -583,9 +584,11 @@ consis_fwd_kernel(const __grid_constant__ ConsisParams P, float* __restrict__ su
 }
 
 // Separate one-block launch (folding it into the forward kernel like smooth_fwd does brought nothing here: 18.5 -> 19.1 us,
-// the block counter is one more same-address atomic for each of the ~1100 short-lived blocks).
+// the block counter is one more same-address atomic for each of the ~1100 short-lived blocks), but as a programmatic
+// dependent of the forward kernel: it is already resident and waiting when the last block of that grid retires.
 __global__ void consis_finalize_kernel(const __grid_constant__ ConsisParams P, const float* __restrict__ sums,
                                        float* __restrict__ loss) {
+  pdl_wait();
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.B; b += gridDim.x * blockDim.x) {
     float acc = 0.0f;
     for (int l = 0; l < P.nlevels; ++l) {
@@ -732,7 +735,7 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
     consis_fwd_kernel<4><<<ceil_div(P.warp_begin[nlevels], kConsisFwdWarps), kConsisFwdWarps * 32, 0, stream>>>(P, sums);
   else
     consis_fwd_kernel<1><<<ceil_div(P.warp_begin[nlevels], kConsisFwdWarps), kConsisFwdWarps * 32, 0, stream>>>(P, sums);
-  consis_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss);
+  UOF_CUDA(launch_dependent(consis_finalize_kernel, dim3(ceil_div(B, 64)), dim3(64), stream, P, (const float*)sums, loss));
   count_launch(2);
   return check_launch("consis_loss_fwd");
 }

@@ -108,6 +108,7 @@ __device__ __forceinline__ SsimTerms ssim_from_sums(const float* s0, const float
 // -------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 photo_loss_fwd_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
+  pdl_trigger();      // the finalize grid is a programmatic dependent (common.cuh)
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   Strip sc;
@@ -237,6 +238,7 @@ __device__ __forceinline__ f2 ssim2(f2 Sx, f2 Sy, f2 Sxx, f2 Syy, f2 Sxy) {
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 photo_loss_fwd_pair_kernel(const __grid_constant__ PhotoParams P, float* __restrict__ sums) {
+  pdl_trigger();      // the finalize grid is a programmatic dependent (common.cuh)
   __shared__ float2 ring_s[kWarpsPerBlock][kFwdPairDepth * 9 * 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int dir = wid & 1;                                   // 0: left / "bwd", 1: right / "fwd"
@@ -339,6 +341,7 @@ photo_loss_fwd_pair_kernel(const __grid_constant__ PhotoParams P, float* __restr
 // is one more same-address atomic per block.
 __global__ void photo_loss_finalize_kernel(const __grid_constant__ PhotoParams P, const float* __restrict__ sums,
                                            float* __restrict__ loss_pixel, float* __restrict__ loss_ssim) {
+  pdl_wait();         // launched while the forward grid is still running; its sums are complete and visible after this
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.T.B; b += gridDim.x * blockDim.x) {
     float lp = 0.0f, ls = 0.0f;
     for (int l = 0; l < P.T.nlevels; ++l) {
@@ -784,7 +787,7 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
     if (int rc = fill_params(P, levels, nlevels, B, 1, false, occ_pair, false, 2, kWarpsPerBlock / 2, 2)) return rc;
     UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
     photo_loss_fwd_pair_kernel<<<ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock / 2), kWarpsPerBlock * 32, 0, stream>>>(P, sums);
-    photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
+    UOF_CUDA(launch_dependent(photo_loss_finalize_kernel, dim3(ceil_div(B, 64)), dim3(64), stream, P, (const float*)sums, loss_pixel, loss_ssim));
     count_launch(2);
     return check_launch("photo_loss_fwd (pair)");
   }
@@ -793,7 +796,7 @@ extern "C" int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, in
   UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 6 + UOF_SUMS_EXTRA) * sizeof(float), stream));
   const int blocks = ceil_div(P.T.warp_begin[nlevels], kWarpsPerBlock);
   photo_loss_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(P, sums);
-  photo_loss_finalize_kernel<<<ceil_div(B, 64), 64, 0, stream>>>(P, sums, loss_pixel, loss_ssim);
+  UOF_CUDA(launch_dependent(photo_loss_finalize_kernel, dim3(ceil_div(B, 64)), dim3(64), stream, P, (const float*)sums, loss_pixel, loss_ssim));
   count_launch(2);
   return check_launch("photo_loss_fwd");
 }

@@ -29,11 +29,14 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // fp32 NCHW tensor viewed as 4-D (W, H, C, B), box (bw, bh, bc, 1), out-of-bounds elements read as zero.
 // Needs a 16-byte aligned base and W % 4 == 0 (global strides must be multiples of 16 bytes).
-inline bool make_nchw_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int bc) {
+// `batch_stride` (floats, 0 = dense C*H*W): lets the map address a channel slice of a wider (B,C',H,W) buffer in place.
+inline bool make_nchw_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int bc,
+                          long long batch_stride = 0) {
   EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u) || (W % 4) != 0) return false;
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u) || (W % 4) != 0 || (batch_stride % 4) != 0) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+  const cuuint64_t bs = batch_stride > 0 ? (cuuint64_t)batch_stride : (cuuint64_t)W * H * C;
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, bs * 4};
   const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,

@@ -118,7 +118,7 @@ class Model_flow(nn.Module):
             # 3B batch and the [left; right] warp sources are views -- no torch.cat of the images anywhere
             feats = self.fpyramid(stacked[0].view(3 * B, 3, H, W))                   # one 3B encoder pass
             parts = [f.split(B, 0) for f in feats]                                   # (left, right, centre)
-            f1 = [torch.cat((c, c), 0) for _, _, c in parts]                         # [centre ; centre]
+            f1 = [c for _, _, c in parts]                                            # centre, paired with both (PWC_tf.forward repeats it)
             f2 = [torch.cat((l, r), 0) for l, r, _ in parts]                         # [left   ; right ]
             pyr_c = [t[2] for t in stacked]
             sources = [t[:2].reshape(2 * B, 3, t.shape[3], t.shape[4]) for t in stacked]
@@ -128,7 +128,7 @@ class Model_flow(nn.Module):
             # split (not three slices): its backward is ONE concatenation of the three gradients instead of three
             # zero-filled full-size tensors plus adds
             parts = [f.split(B, 0) for f in feats]                                   # (left, centre, right)
-            f1 = [torch.cat((c, c), 0) for _, c, _ in parts]
+            f1 = [c for _, c, _ in parts]
             f2 = [torch.cat((l, r), 0) for l, _, r in parts]
             pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)              # one launch, triplet read in place
             sources = [torch.cat((pyr_l[s], pyr_r[s]), 0) for s in range(S)]

@@ -104,21 +104,27 @@ class PWC_tf(nn.Module):
         return getattr(self, 'predict_flow%d' % lvl)(torch.cat((x3b, x4a), 1)), x4b
 
     def forward(self, feature_list_1, feature_list_2, img_hw):
-        flows, up, x4 = {}, None, None
+        """pwc_tf.py:108-179.  The first feature list may carry 1/rep of the second one's batch: it is then taken as
+        repeated along the batch (Model_flow.forward pairs [centre; centre] with [left; right]) without being copied."""
+        flows, flow, x4 = {}, None, None
+        fused = self.corr == self.corr_cuda          # default seam: the fused decoder-input node (ops.decoder_input)
         for lvl in (6, 5, 4, 3, 2):
             c1, c2 = feature_list_1[lvl - 1], feature_list_2[lvl - 1]
-            if up is None:
-                flow, x4 = self._level(lvl, self.corr(c1, c2))
+            rep = c2.shape[0] // c1.shape[0]
+            if flow is None:
+                flow, x4 = self._level(lvl, self.corr(c1.repeat(rep, 1, 1, 1) if rep > 1 else c1, c2))
             else:
-                if self.corr == self.corr_cuda:      # default seam: cost volume written straight into the concat buffer
-                    x = ops.corr_concat(c1, self.warp(c2, up), up)
+                if fused and c2.shape[2] == 2 * flow.shape[2] and c2.shape[3] == 2 * flow.shape[3]:
+                    # up-sampling, warp, cost volume and the concatenation as one node: the cost volume is written straight
+                    # into the concat buffer and reads c1 from it, `up` is written into it by the up-sampling kernel
+                    x, up = ops.decoder_input(c1, c2, flow, self.align_corners)
                 else:                                # a user-installed corr keeps the reference's three-step form
-                    x = torch.cat((self.corr(c1, self.warp(c2, up)), c1, up), 1)
+                    up = ops.upsample_bilinear_scaled(flow, (2 * flow.shape[2], 2 * flow.shape[3]), 2.0)      # pwc_tf.py:119
+                    c1r = c1.repeat(rep, 1, 1, 1) if rep > 1 else c1
+                    x = torch.cat((self.corr(c1r, self.warp(c2, up)), c1r, up), 1)
                 res, x4 = self._level(lvl, x)
                 flow = res + up
             flows[lvl] = flow
-            if lvl > 2:
-                up = ops.upsample_bilinear_scaled(flow, (2 * flow.shape[2], 2 * flow.shape[3]), 2.0)      # pwc_tf.py:119
         t = torch.cat((flows[2], x4), 1)
         for i in range(1, 7):
             t = getattr(self, 'dc_conv%d' % i)(t)

@@ -136,6 +136,87 @@ def corr_concat(c1: torch.Tensor, c2_warped: torch.Tensor, up_flow: torch.Tensor
     return _CostVolumeConcat.apply(c1, c2_warped, up_flow)
 
 
+class _DecoderInput(torch.autograd.Function):
+    """Input of one decoder level, pwc_tf.py:119-123 (and :132-136, :144-148, :157-161), as ONE autograd node:
+
+        up = 2 * F.interpolate(flow_prev, scale_factor=2, mode='bilinear')
+        x  = torch.cat((corr(c1, warp(c2, up)), c1, up), 1)            -> (x, up)
+
+    SURVEY 8(f) rank 2, "decoder glue fusion".  `c` may carry 1/rep of the batch of `c2` (the training step's first
+    feature list is [centre; centre]): it is stored ONCE, broadcast into the `c1` slice of the concat buffer, and the cost
+    volume reads its first operand in place from that slice (batch stride of the buffer) -- no torch.cat((c, c)) and no
+    copy of c1 into the concat.  The up-sampling kernel writes `up` both densely (for the warp and the residual add) and
+    into the buffer's last two channels.  Backward: the cost-volume kernel adds the `c1` slice gradient in its epilogue,
+    the up-sampling backward sums its three gradient sources (warp, concat slice, residual) while it gathers."""
+
+    @staticmethod
+    def forward(ctx, c, c2, flow_prev, align_corners):
+        c, c2, fp = c.contiguous(), c2.contiguous(), flow_prev.contiguous()
+        B, C, H, W = c2.shape
+        B1 = c.shape[0]
+        assert B % B1 == 0 and tuple(c.shape[1:]) == (C, H, W) and tuple(fp.shape) == (B, 2, H // 2, W // 2)
+        nd = NUM_DISPLACEMENTS
+        ctot, plane = nd + C + 2, H * W
+        dev = c2.device
+        x = torch.empty((B, ctot, H, W), device=dev, dtype=torch.float32)
+        up = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        c2w = torch.empty_like(c2)
+        flags = _coord_flags(align_corners)
+        elt = x.element_size()
+        with torch.cuda.device_of(c2):
+            st = _stream(c2)
+            _lib.call('uof_upsample_bilinear_fwd2', _p(fp), _p(up), ctypes.c_void_p(x.data_ptr() + (nd + C) * plane * elt), 2,
+                      ctot * plane, B * 2, H // 2, W // 2, H, W, 2.0, st)
+            _lib.call('uof_warp_fwd', _p(c2), _p(up), _p(c2w), B, C, H, W, 0, flags, 0, st)
+            # c -> the c1 slice of every replica (one broadcasting copy)
+            x.view(B // B1, B1, ctot, H, W)[:, :, nd:nd + C].copy_(c.unsqueeze(0).expand(B // B1, B1, C, H, W))
+            _lib.call('uof_cost_volume_fwd_ex', ctypes.c_void_p(x.data_ptr() + nd * plane * elt), ctot * plane, _p(c2w), _p(x),
+                      B, C, H, W, ctot * plane, st)
+        ctx.save_for_backward(x, c2, c2w, up)
+        ctx.dims = (B, B1, C, H, W, flags)
+        return x, up
+
+    @staticmethod
+    def backward(ctx, gx, g_up):
+        x, c2, c2w, up = ctx.saved_tensors
+        B, B1, C, H, W, flags = ctx.dims
+        nd = NUM_DISPLACEMENTS
+        ctot, plane = nd + C + 2, H * W
+        dev = x.device
+        if gx is None:
+            gx = torch.zeros_like(x)
+        gx = gx.contiguous()
+        if g_up is not None:
+            g_up = g_up.contiguous()
+        elt = x.element_size()
+        g1, g2w = torch.empty((B, C, H, W), device=dev, dtype=torch.float32), torch.empty_like(c2w)
+        gc2, gflow = torch.empty_like(c2), torch.empty_like(up)
+        gprev = torch.empty((B, 2, H // 2, W // 2), device=dev, dtype=torch.float32)
+        _alert_not_deterministic('uof_warp_bwd (gradient w.r.t. the warped tensor)')
+        with torch.cuda.device_of(x):
+            st = _stream(x)
+            _lib.call('uof_cost_volume_bwd_ex', _p(gx), ctot * plane, ctypes.c_void_p(x.data_ptr() + nd * plane * elt), ctot * plane,
+                      _p(c2w), ctypes.c_void_p(gx.data_ptr() + nd * plane * elt), ctot * plane, _p(g1), _p(g2w), B, C, H, W, st)
+            _lib.call('uof_warp_bwd', _p(g2w), _p(c2), _p(up), _p(gc2), _p(gflow), B, C, H, W, 0, flags, 0, st)
+            _lib.call('uof_upsample_bilinear_bwd3', _p(gflow), ctypes.c_void_p(gx.data_ptr() + (nd + C) * plane * elt), 2,
+                      ctot * plane, _p(g_up), _p(gprev), B * 2, H // 2, W // 2, H, W, 2.0, st)
+        gc = g1 if B1 == B else g1.view(B // B1, B1, C, H, W).sum(0)
+        return gc, gc2, gprev, None
+
+
+def decoder_input(c: torch.Tensor, c2: torch.Tensor, flow_prev: torch.Tensor, align_corners: bool | None = None):
+    """-> (x, up) with up = 2 * interpolate(flow_prev, x2) and x = cat((corr(c1, warp(c2, up)), c1, up), 1), where c1 is
+    `c` repeated along the batch to c2's batch size (pwc_tf.py:119-123), fused (see _DecoderInput)."""
+    _require_cuda(c, c2, flow_prev)
+    B, C, H, W = c2.shape
+    if (c2.shape[0] % c.shape[0] or tuple(c.shape[1:]) != (C, H, W)
+            or tuple(flow_prev.shape) != (B, 2, H // 2, W // 2) or H % 2 or W % 2):
+        raise ValueError('decoder_input: c %r, c2 %r and flow_prev %r do not form a decoder level'
+                         % (tuple(c.shape), tuple(c2.shape), tuple(flow_prev.shape)))
+    ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+    return _DecoderInput.apply(c, c2, flow_prev, ac)
+
+
 # --------------------------------------------------------------------------------------- a2/a3
 def _is_channels_last(x):
     return (x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] > 1 and not x.is_contiguous()
