@@ -239,6 +239,36 @@ int uof_fb_consistency_mask(const float* flow_fwd, const float* flow_rev, float*
                             int B, int H, int W, float alpha, float beta, int align_corners,
                             uof_stream_t stream);
 
+/* ---- the data formats either side of the hot path ------------------------------------------------ */
+
+/* Input pipeline.  Replaces KITTI_Prepared.resize_img / random_flip_img / preprocess_img and the transpose + .float() of
+ * __getitem__ (core/dataset/kitti_prepared.py:63-91,146-153): the decoded uint8 strip of `nimg` vertically stacked BGR
+ * images, (nimg*H0, W0, 3) per sample with `src_batch_stride` BYTES between samples, is cut into its images; each is resized
+ * to (H, W) exactly as cv2.resize(INTER_LINEAR) does on 8-bit data (bit-exact: 11-bit fixed-point coefficients, OpenCV's
+ * rounding), re-stacked, mirrored horizontally where flip[b] != 0 (flip: B device bytes, NULL = never), divided by 255 and
+ * written as the (B, 3, nimg*H, W) fp32 batch Model_flow.forward takes. */
+int uof_preprocess_u8(const unsigned char* src, long long src_batch_stride, const unsigned char* flip, float* out,
+                      int B, int nimg, int H0, int W0, int H, int W, uof_stream_t stream);
+
+/* KITTI 16-bit flow PNG arithmetic (core/evaluation/flowlib.py:107-138) on the decoded (H,W,3) uint16 array [u, v, valid]:
+ * decode: flow[...,0:2] = (raw - 2^15) / 64 where valid, else 0; flow[...,2] = valid      -> (H,W,3) fp32
+ * encode: raw = [clip(u*64 + 2^15, 0, 65535), clip(v*64 + 2^15, 0, 65535), 1] truncated; `flow` has `channel_stride` >= 2
+ *         floats per pixel (2 for (H,W,2), 3 for a decoded (H,W,3) array). */
+int uof_flow_png_decode(const unsigned short* raw, float* flow, long long npix, uof_stream_t stream);
+int uof_flow_png_encode(const float* flow, int channel_stride, unsigned short* raw, long long npix, uof_stream_t stream);
+
+/* Flow evaluation of one image.  Replaces the loop body of eval_flow_avg and calculate_error_rate
+ * (core/evaluation/evaluate_flow.py:85-160): pred (2,h,w) planar fp32 in network-resolution pixels is rescaled by
+ * (W/img_w, H/img_h), resized to the ground-truth size like cv2.resize(float32, INTER_LINEAR), and compared with
+ * gt (H,W,3) fp32 [u, v, valid]; noc_mask (H,W); moving_mask (H,W) or NULL.  sums: 13 DEVICE doubles, zero-filled here:
+ *   [0] sum epe*valid  [1] sum valid  [2] sum epe*noc  [3] sum noc  [4] sum epe*(valid-noc)  [5] sum (valid-noc)
+ *   [6] outliers(valid)  [7] outliers(valid*move)  [8] sum valid*move  [9] outliers(valid*(1-move))
+ *   [10] sum valid*(1-move)  [11] sum epe*valid*move  [12] sum epe*valid*(1-move)
+ * with outlier = epe*m > 3 and epe*m / max(|gt|, 1e-10) > 0.05. */
+#define UOF_FLOW_EVAL_SUMS 13
+int uof_flow_eval(const float* pred, int h, int w, const float* gt, const float* noc_mask, const float* moving_mask,
+                  int H, int W, int img_h, int img_w, double* sums, uof_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,18 @@ COEF_BITS = 11                      # INTER_RESIZE_COEF_BITS
 COEF_SCALE = 1 << COEF_BITS         # 2048
 
 
+def synthetic_strip(h0: int, w0: int, nimg: int = 3, seed: int = 0):
+    """Deterministic uint8 test strip (nimg*h0, w0, 3) built from integer arithmetic only (no RNG state, no cv2), so the
+    golden script and the tests construct the same bytes anywhere: smooth ramps, a checker texture and hashed noise."""
+    y = np.arange(nimg * h0, dtype=np.int64)[:, None, None]
+    x = np.arange(w0, dtype=np.int64)[None, :, None]
+    c = np.arange(3, dtype=np.int64)[None, None, :]
+    ramp = (y * (3 + c) + x * (5 - c)) // 4
+    checker = (((y // 6) + (x // 9)) % 2) * 70
+    hashed = ((y * 73856093 + x * 19349663 + (c + seed) * 83492791) ^ ((y * x + seed) >> 3)) % 61
+    return ((ramp + checker + hashed) % 256).astype(np.uint8)
+
+
 def linear_coeffs(dst: int, src: int, vertical: bool):
     """Source indices and fractions of cv2's bilinear resize along one axis (resize.cpp, `resizeGeneric_` set-up):
     f = (float)((d + 0.5) * (double)src / dst - 0.5); s = floor(f); f -= s.  Along x a source index outside the row sets

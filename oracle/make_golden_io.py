@@ -10,8 +10,8 @@ not installed here and are only needed to open PNG files / colour-code flow imag
 under those names; the dataset class is
 instantiated with `object.__new__` because its constructor reads a file list.  The oracle (oracle/io_ops.py) is checked
 against every recorded value and, separately, against cv2 itself on random shapes; the script prints both.
-Fixtures are small (seeded synthetic images at reduced sizes); the KITTI-size resize is recorded as a CRC32 of the output
-plus two sample rows.
+Fixtures are small (seeded synthetic images at reduced sizes); the KITTI- and Sintel-size resizes are recorded as
+CRC32s of the output for the integer test strip of oracle.io_ops.synthetic_strip.
 """
 from __future__ import annotations
 
@@ -80,16 +80,18 @@ def main():
         print('%-22s oracle == reference (bit-exact), %s -> %s' % (name, img.shape, out['out_flip0'].shape))
 
     # ---- KITTI-size resize: CRC + sample rows ----------------------------------------------------------------------
-    img = synth_triplet(rng, 375, 1242)
-    ds.random_flip_img = lambda im: im
-    ref = ds.preprocess_img(img, (256, 832)).transpose(2, 0, 1).astype(np.float32)
-    mine = IO.preprocess_img(img, (256, 832), False)
-    assert np.array_equal(ref, mine)
-    seed_note = np.array([20261017], dtype=np.int64)
-    np.savez_compressed(os.path.join(args.out, 'io_preprocess_kitti.npz'), seed=seed_note,
-                        crc=np.array([zlib.crc32(ref.tobytes())], dtype=np.int64), rows=ref[:, [0, 300, 767]][:, :, ::8],
-                        img_crc=np.array([zlib.crc32(img.tobytes())], dtype=np.int64))
-    print('io_preprocess_kitti    oracle == reference (bit-exact) at 3x375x1242 -> 3x256x832, crc %08x' % zlib.crc32(ref.tobytes()))
+    for tag, (h0, w0, hw) in {'kitti': (375, 1242, (256, 832)), 'sintel': (436, 1024, (448, 1024))}.items():
+        img = IO.synthetic_strip(h0, w0, 3, seed=h0)
+        crcs = []
+        for flip in (0, 1):
+            ds.random_flip_img = (lambda im, f=flip: cv2.flip(im, 1) if f else im)
+            ref = ds.preprocess_img(img, hw).transpose(2, 0, 1).astype(np.float32)
+            assert np.array_equal(ref, IO.preprocess_img(img, hw, bool(flip)))
+            crcs.append(zlib.crc32(np.ascontiguousarray(ref).tobytes()))
+        np.savez_compressed(os.path.join(args.out, 'io_preprocess_%s.npz' % tag), shape=np.array([h0, w0, hw[0], hw[1]]),
+                            crc=np.array(crcs, dtype=np.int64), img_crc=np.array([zlib.crc32(img.tobytes())], dtype=np.int64))
+        print('io_preprocess_%-9s oracle == reference (bit-exact) at 3x%dx%d -> 3x%dx%d, crc %08x / %08x (flipped)'
+              % (tag, h0, w0, hw[0], hw[1], crcs[0], crcs[1]))
 
     # ---- cv2 itself, random shapes ---------------------------------------------------------------------------------
     bad = 0

@@ -75,6 +75,10 @@ SIGNATURES = {
     'uof_splat_targets': [_P, _P, _I, _I, _I, _P],
     'uof_clamp01': [_P, _LL, _P],
     'uof_fb_consistency_mask': [_P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    'uof_preprocess_u8': [_P, _LL, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'uof_flow_png_decode': [_P, _P, _LL, _P],
+    'uof_flow_png_encode': [_P, _I, _P, _LL, _P],
+    'uof_flow_eval': [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
 }
 DIAGNOSTICS = {'uof_abi_version': (ctypes.c_int, []), 'uof_last_error': (ctypes.c_char_p, []),
                'uof_launch_count': (ctypes.c_longlong, [])}

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libuof_b200.so')
 SOURCES = ['runtime.cu', 'cost_volume.cu', 'cost_volume_tma.cu', 'cost_volume_small.cu', 'cost_volume_tc.cu', 'warp.cu', 'photo_loss.cu', 'ssim_map.cu', 'flow_losses.cu',
-           'seams.cu', 'splat.cu', 'pyramid.cu', 'act.cu', 'upsample.cu']
+           'seams.cu', 'splat.cu', 'pyramid.cu', 'act.cu', 'upsample.cu', 'io_pipeline.cu']
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

@@ -318,7 +318,7 @@ cost_volume_fwd_tma_persistent_kernel(const __grid_constant__ CUtensorMap map1, 
 // blockIdx.y selects the role:
 //   0: gf1[c,p] = 1/C * sum_d gout[d,p]          * f2[c,p+d]
 //   1: gf2[c,q] = 1/C * sum_d gout[flip(d),q+d]  * f1[c,q+d]     (d -> -d re-indexed as flip)
-template <class T>
+template <class T, bool ADD>
 __global__ void __launch_bounds__(NT, 2)
 cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                            const float* __restrict__ gout, long long gout_bs, const float* __restrict__ gadd,
@@ -364,7 +364,8 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
 
   float* dst_b = (mirror ? gf2 : gf1) + (size_t)b * C * H * W;
   const float* gb = gout + (size_t)b * gout_bs;
-  const float* add_b = (!mirror && gadd) ? gadd + (size_t)b * gadd_bs : nullptr;   // concat-slice gradient folded into gf1
+  // ADD: the concat-slice gradient `gadd` is folded into gf1 (role 0 only)
+  const float* add_b = (ADD && !mirror) ? gadd + (size_t)b * gadd_bs : nullptr;
   const size_t plane = (size_t)H * W;
   const int y = y0 + ty, x = x0 + PX * gx;
 
@@ -403,6 +404,24 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
     mbar_wait(full + s, (j / NSTAGE) & 1);
     const float* w_base = smem + s * S2 + (ty + dg * DYG) * HTW + PX * gx;
     float* rbuf = red + (j & 1) * kRed;
+    const int k = k_begin + j;
+    // the slice gradient of this thread's output elements is fetched at the top of the slab, so its latency hides behind
+    // the slab's FMAs (loaded inside the reduction loop it cost 19 us at 16x32x64x208: every slab ended on an exposed L2
+    // round trip)
+    constexpr int kPerThread = (CK * TH * (TW / 4) + NT - 1) / NT;
+    float4 addv[ADD ? kPerThread : 1];
+    if (ADD) {
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u) {
+        const int e = tid + u * NT;
+        const int q = e % (TW / 4), r = (e / (TW / 4)) % TH, cc = e / ((TW / 4) * TH);
+        const int c = k * CK + cc, yy = y0 + r, xx = x0 + 4 * q;
+        addv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_b && e < CK * TH * (TW / 4) && c < C && yy < H && xx < W)
+          addv[u] = __ldg(reinterpret_cast<const float4*>(add_b + ((size_t)c * H + yy) * W + xx));
+      }
+    }
+
 #pragma unroll
     for (int cc = 0; cc < CK; ++cc) {
       float part[PX] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -423,8 +442,10 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
     if (lane == 0) mbar_arrive(empty + s);
     __syncthreads();   // partial sums of the three dy-groups are in rbuf (double-buffered: one barrier per slab)
 
-    const int k = k_begin + j;
-    for (int e = tid; e < CK * TH * (TW / 4); e += NT) {
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int e = tid + u * NT;
+      if (e >= CK * TH * (TW / 4)) break;
       const int q = e % (TW / 4), r = (e / (TW / 4)) % TH, cc = e / ((TW / 4) * TH);
       const int c = k * CK + cc, yy = y0 + r, xx = x0 + 4 * q;
       if (c >= C || yy >= H || xx >= W) continue;
@@ -436,9 +457,8 @@ cost_volume_bwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __gri
         sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
       }
       float4 res = make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
-      if (add_b) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(add_b + ((size_t)c * H + yy) * W + xx));
-        res.x += a.x; res.y += a.y; res.z += a.z; res.w += a.w;
+      if (ADD) {
+        res.x += addv[u].x; res.y += addv[u].y; res.z += addv[u].z; res.w += addv[u].w;
       }
       *reinterpret_cast<float4*>(dst_b + ((size_t)c * H + yy) * W + xx) = res;
     }
@@ -546,7 +566,7 @@ int launch_bwd(const float* gout, long long gout_bs, const float* f1, long long 
   const int tx = ceil_div(W, T::TW), ty = ceil_div(H, T::TH);
   const int csplit = pick_split((long long)tx * ty * B * 2, ceil_div(C, CK));
   UOF_REQUIRE((long long)B * csplit <= 65535, "cost_volume_bwd: grid too large");
-  auto kern = cost_volume_bwd_tma_kernel<T>;
+  auto kern = gadd ? cost_volume_bwd_tma_kernel<T, true> : cost_volume_bwd_tma_kernel<T, false>;
   UOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<T>()));
   kern<<<dim3(tx * ty, 2, B * csplit), NT, bwd_smem<T>(), stream>>>(m1, m2, gout, gout_bs, gadd, gadd_bs, gf1, gf2, C, H, W,
                                                                     tx, csplit, 1.0f / (float)C);
