@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--overlap-tail-ms', type=float, default=0.0,
+                    help='N > 1: all-reduce the gradients that are ready this many ms before backward ends from a hook, '
+                         'overlapped with the rest of backward (0 = one all-reduce after backward)')
     ap.add_argument('--ddp', action='store_true',
                     help='N > 1: eager DistributedDataParallel step instead of the graphed flat all-reduce step')
     ap.add_argument('--profile-step', action='store_true',
@@ -164,6 +167,12 @@ def algorithmic_bytes(name, args):
     if name == 'uof_bias_lrelu_fwd':            # read + write the activation in place
         B, C, H, W = args[2:6]
         return 8 * B * C * H * W
+    if name == 'uof_bias_lrelu_fwd2':           # read the convolution output, write one or two destinations
+        B, C, H, W = (int(v) for v in args[6:10])
+        return (3 if args[4] else 2) * 4 * B * C * H * W
+    if name == 'uof_bias_lrelu_bwd3':           # read g1 (+ g2) and y, write gx
+        B, C, H, W = (int(v) for v in args[8:12])
+        return (4 if args[2] else 3) * 4 * B * C * H * W
     if name == 'uof_bias_lrelu_bwd2':           # read g1 (+ g2) and y, write gx
         B, C, H, W = (int(v) for v in args[7:11])
         return (4 if args[2] else 3) * 4 * B * C * H * W
@@ -213,6 +222,10 @@ class KernelObserver:
                 key += '+gx' if args[3].value else ''
         elif name.startswith('uof_upsample_bilinear'):
             key = '%s[%s]' % (name, 'x'.join(str(int(d)) for d in args[2:7]))
+        elif name == 'uof_bias_lrelu_fwd2':
+            key = 'uof_bias_lrelu_fwd[%s]%s' % ('x'.join(str(int(d)) for d in args[6:10]), '+d2' if args[4] else '')
+        elif name == 'uof_bias_lrelu_bwd3':
+            key = 'uof_bias_lrelu_bwd[%s]%s' % ('x'.join(str(int(d)) for d in args[8:12]), '+g2' if args[2] else '')
         elif name == 'uof_bias_lrelu_bwd2':      # same key as the one-gradient form, '+g2' when two gradients are summed
             key = 'uof_bias_lrelu_bwd[%s]%s' % ('x'.join(str(int(d)) for d in args[7:11]), '+g2' if args[2] else '')
         elif name.startswith('uof_bias_lrelu'):
@@ -249,6 +262,15 @@ class KernelObserver:
                         'frac': round(gbs / peak_gbs, 4)})
         out.sort(key=lambda r: -r['total_ms'])
         return out
+
+
+def exchange_note(graphed):
+    ex = graphed.exchange
+    if ex is not None and ex.n_early:
+        return ('flat gradient buffer in the CUDA graph, two NCCL all-reduces: %.1f MB (%d tensors, the decoder) launched from a '
+                'gradient hook and overlapped with the rest of backward, %.1f MB after backward'
+                % (ex.n_early * 4 / 1e6, ex._early_total, (ex.flat.numel() - ex.n_early) * 4 / 1e6))
+    return 'one flat NCCL all-reduce of the gradients inside the CUDA graph'
 
 
 # ------------------------------------------------------------------------------ reference arms
@@ -468,7 +490,8 @@ def run_b200(args):
     launches_per_graph_step = 0
     if use_graph:
         n_before = _lib.launch_count()
-        graphed = T.GraphedTrainStep(model, resident[0], weights, cfg.lr, warmup=3, allreduce=world > 1)
+        graphed = T.GraphedTrainStep(model, resident[0], weights, cfg.lr, warmup=3, allreduce=world > 1,
+                                     overlap=args.overlap_tail_ms > 0, overlap_tail_ms=args.overlap_tail_ms)
         launches_per_graph_step = (_lib.launch_count() - n_before) // 4      # 3 eager warm-ups + 1 capture pass
         step = graphed
     else:
@@ -588,7 +611,7 @@ def run_b200(args):
             'config': workload_config(B, world, H, W, scaling_of(args)),
             'triplets_per_s': round(B * world / (ms_step * 1e-3), 3),
             'execution': {'cuda_graph': bool(use_graph),
-                          'gradient_exchange': (('one flat NCCL all-reduce of the gradients inside the CUDA graph' if use_graph else
+                          'gradient_exchange': ((exchange_note(graphed) if use_graph else
                                                  'DistributedDataParallel, NCCL') if world > 1 else None)},
             'clocks': clocks,
             'e2e': {'value': round(fp_per_step / (ms_e2e * 1e-3), 3), 'unit': UNIT, 'ms_per_step': round(ms_e2e, 3),

@@ -200,6 +200,18 @@ int uof_bias_lrelu_bwd2(const float* g1, long long g1_batch_stride, const float*
                         const float* y, float* gx, float* gbias, int B, int C, int H, int W, float slope,
                         uof_stream_t stream);
 
+/* Concat-free dense block (pwc_tf.py:113-118: x = cat((conv(x), x), 1) five times per level): the activation of the dense
+ * convolution output `in` is written to dst1 and, when dst2 != NULL, also to dst2 -- (B,C,H,W) views with explicit batch
+ * strides (floats), i.e. channel slices of pre-allocated concat buffers (dst1 == in with a dense stride is the in-place
+ * form).  Every activation of the decoder is concatenated twice; writing it where the concatenations will be read removes
+ * the torch.cat copy kernels (7 -> 4 passes over each activation).  bwd3 = bwd2 with the saved activation `y` read
+ * through a batch stride as well (it lives in one of those buffers). */
+int uof_bias_lrelu_fwd2(const float* in, const float* bias, float* dst1, long long dst1_batch_stride, float* dst2,
+                        long long dst2_batch_stride, int B, int C, int H, int W, float slope, uof_stream_t stream);
+int uof_bias_lrelu_bwd3(const float* g1, long long g1_batch_stride, const float* g2, long long g2_batch_stride,
+                        const float* y, long long y_batch_stride, float* gx, float* gbias, int B, int C, int H, int W,
+                        float slope, uof_stream_t stream);
+
 /* a11 glue: bilinear up-sampling (align_corners = False, ATen upsample_bilinear2d semantics) fused with a scale factor:
  * out = scale * interpolate(in).  Replaces `F.interpolate(flow, scale_factor=2.0, mode='bilinear') * 2.0`
  * (pwc_tf.py:119,132,144,157) and `F.interpolate(flow * 4.0, [h, w], mode='bilinear')` (pwc_tf.py:174-177).

@@ -41,11 +41,26 @@ def _worker(rank, world, port, out_dir):
         T.total_loss(model2(x[rank:rank + 1]), w).backward()
         ex.allreduce()
     assert all(p.grad.data_ptr() >= ex.flat.data_ptr() for p in model2.parameters()), 'grads must stay views of the flat buffer'
-    flat = ex.flat.clone()
+    flat = torch.cat([p.grad.flatten() for p in model2.parameters()])
+    # the overlapped form: observe one backward, re-lay the buffer in completion order, early chunk reduced from a hook
+    torch.manual_seed(0)
+    model3 = omodel.Model_flow(omodel.Cfg)
+    ex3 = T.FlatGradAllReduce(list(model3.parameters()))
+    ex3.observe()
+    ex3.zero()
+    T.total_loss(model3(x[rank:rank + 1]), w).backward()
+    n_early = ex3.plan_overlap()
+    assert 0 < n_early < len(ex3.params) and 0 < ex3.n_early < ex3.flat.numel()
+    for _ in range(2):
+        ex3.zero()
+        T.total_loss(model3(x[rank:rank + 1]), w).backward()
+        assert ex3._early_done, 'the early chunk must have been launched from the gradient hooks during backward'
+        ex3.allreduce()
+    flat_overlap = torch.cat([p.grad.flatten() for p in model3.parameters()])
     # max-over-ranks reduction used by bench.py for timing
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    torch.save({'grads': grads, 'flat': flat, 'tmax': t}, os.path.join(out_dir, 'rank%d.pt' % rank))
+    torch.save({'grads': grads, 'flat': flat, 'flat_overlap': flat_overlap, 'tmax': t}, os.path.join(out_dir, 'rank%d.pt' % rank))
     dist.destroy_process_group()
 
 
@@ -69,6 +84,10 @@ def test_ddp_gradients_equal_single_process(tmp_path):
     assert torch.equal(r0['flat'], r1['flat'])
     err = float((r0['flat'] - ref).norm() / ref.norm())
     assert err < 1e-5, err
+    # ... == the two-chunk overlapped exchange
+    assert torch.equal(r0['flat_overlap'], r1['flat_overlap'])
+    err = float((r0['flat_overlap'] - r0['flat']).norm() / ref.norm())
+    assert err < 1e-6, err
 
 
 def test_loss_weights_and_total_loss():

@@ -162,6 +162,47 @@ def test_conv_block_forked_activation(U, h, w):
     assert_close(gc, gd, 1e-5, 'forked conv block, single consumer')
 
 
+@pytest.mark.parametrize('hw', [(8, 12), (7, 9), (16, 52)])
+def test_concat_free_dense_block_matches_torch(U, hw):
+    """ops.bias_leaky_relu_to + ops.cat_alias (uof_bias_lrelu_fwd2 / _bwd3): the dense-block pattern of pwc_tf.py:113-118 --
+    activations written straight into channel slices of pre-allocated concat buffers, torch.cat replaced by an alias --
+    against conv2d + leaky_relu + torch.cat in plain PyTorch: values, input gradient and every weight / bias gradient."""
+    import torch.nn.functional as F
+    H, W = hw
+    B, cin, c0, c1, c2 = 3, 6, 8, 12, 4
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    ws = [torch.randn(c, ci, 3, 3, generator=g).cuda() * 0.2 for c, ci in ((c0, cin), (c1, c0), (c2, c0 + c1))]
+    bs = [torch.randn(c, generator=g).cuda() for c in (c0, c1, c2)]
+    ct = torch.randn(B, c1 + c2, H, W, generator=g).cuda()
+
+    def ref(x, ws, bs):
+        a0 = F.leaky_relu(F.conv2d(x, ws[0], bs[0], padding=1), 0.1)
+        a1 = F.leaky_relu(F.conv2d(a0, ws[1], bs[1], padding=1), 0.1)
+        a2 = F.leaky_relu(F.conv2d(torch.cat((a0, a1), 1), ws[2], bs[2], padding=1), 0.1)
+        return torch.cat((a1, a2), 1)
+
+    def mine(x, ws, bs):
+        new = lambda c: torch.empty((B, c, H, W), device='cuda')
+        b01, b12 = new(c0 + c1), new(c1 + c2)
+        a0a, a0b = U.ops.bias_leaky_relu_to(F.conv2d(x, ws[0], None, padding=1), bs[0], [(None, 0), (b01, 0)])
+        a1a, a1b = U.ops.bias_leaky_relu_to(F.conv2d(a0a, ws[1], None, padding=1), bs[1], [(b01, c0), (b12, 0)])
+        (a2,) = U.ops.bias_leaky_relu_to(F.conv2d(U.ops.cat_alias(b01, (a0b, a1a)), ws[2], None, padding=1), bs[2], [(b12, c1)])
+        return U.ops.cat_alias(b12, (a1b, a2))
+
+    leaves = lambda: ([x.clone().requires_grad_(True)], [w.clone().requires_grad_(True) for w in ws], [b.clone().requires_grad_(True) for b in bs])
+    (xr,), wr, br = leaves()
+    (xm,), wm, bm = leaves()
+    yr, ym = ref(xr, wr, br), mine(xm, wm, bm)
+    assert_close(ym, yr, 1e-5, 'concat-free block fwd')
+    gr = torch.autograd.grad((yr * ct).sum(), [xr] + wr + br)
+    gm = torch.autograd.grad((ym * ct).sum(), [xm] + wm + bm)
+    for a, b_, what in zip(gm, gr, ['x', 'w0', 'w1', 'w2', 'b0', 'b1', 'b2']):
+        assert_close(a, b_, 2e-5, 'concat-free block grad ' + what)
+    with pytest.raises(AssertionError):                       # parts that are not the buffer's slices are refused
+        U.ops.cat_alias(torch.empty(B, 4, H, W, device='cuda'), (torch.empty(B, 2, H, W, device='cuda'),) * 2)
+
+
 @pytest.mark.parametrize('shape', [(2, 8, 6, 9), (3, 17, 33, 70)] + LEVEL_SHAPES)
 def test_cost_volume_ex_strided_operand_and_folded_gradient(U, shape):
     """uof_cost_volume_fwd_ex / _bwd_ex: f1 read in place from a channel slice of a wider buffer and the

@@ -63,6 +63,8 @@ SIGNATURES = {
     'uof_bias_lrelu_fwd': [_P, _P, _I, _I, _I, _I, _F, _P],
     'uof_bias_lrelu_bwd': [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     'uof_bias_lrelu_bwd2': [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    'uof_bias_lrelu_fwd2': [_P, _P, _P, _LL, _P, _LL, _I, _I, _I, _I, _F, _P],
+    'uof_bias_lrelu_bwd3': [_P, _LL, _P, _LL, _P, _LL, _P, _P, _I, _I, _I, _I, _F, _P],
     'uof_upsample_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
     'uof_upsample_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _F, _P],
     'uof_upsample_bilinear_fwd2': [_P, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _P],

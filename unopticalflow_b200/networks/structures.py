@@ -27,10 +27,14 @@ class ConvLReLU(nn.Sequential):
     bias + LeakyReLU kernel (in place), whose backward also produces the bias gradient.  Like every other operator of
     the package it has no CPU path."""
 
-    def forward(self, x, fork=False):
-        """`fork=True`: return the activation twice, one tensor per consumer (ops._BiasLeakyReLU)."""
+    def forward(self, x, fork=False, dsts=None):
+        """`fork=True`: return the activation twice, one tensor per consumer (ops._BiasLeakyReLU).
+        `dsts`: write the activation to one or two `(buffer, channel_offset)` destinations instead (`(None, 0)` = in place)
+        and return one tensor per destination (ops.bias_leaky_relu_to) -- the concat-free dense block of PWC_tf._level."""
         cv, act = self[0], self[1]
         y = F.conv2d(x, cv.weight, None, cv.stride, cv.padding, cv.dilation, cv.groups)
+        if dsts is not None:
+            return ops.bias_leaky_relu_to(y, cv.bias, dsts, act.negative_slope)
         return ops.bias_leaky_relu_(y, cv.bias, act.negative_slope, fork)
 
 
@@ -94,14 +98,26 @@ class PWC_tf(nn.Module):
         return ops.warp_flow(x, flow, use_mask=False, align_corners=self.align_corners)
 
     def _level(self, lvl, x):
-        # pwc_tf.py:113-118 etc.; every activation has two consumers, hence the forks (one tensor per consumer, so that
-        # the fused LeakyReLU backward receives the two gradients separately and sums them itself)
-        x0a, x0b = getattr(self, 'conv%d_0' % lvl)(x, fork=True)
-        x1a, x1b = getattr(self, 'conv%d_1' % lvl)(x0a, fork=True)
-        x2a, x2b = getattr(self, 'conv%d_2' % lvl)(torch.cat((x0b, x1a), 1), fork=True)
-        x3a, x3b = getattr(self, 'conv%d_3' % lvl)(torch.cat((x1b, x2a), 1), fork=True)
-        x4a, x4b = getattr(self, 'conv%d_4' % lvl)(torch.cat((x2b, x3a), 1), fork=True)
-        return getattr(self, 'predict_flow%d' % lvl)(torch.cat((x3b, x4a), 1)), x4b
+        """pwc_tf.py:113-118 etc.: the five-convolution block whose inputs are concatenations of the two previous
+        activations.  Every activation has two consumers; it is written once to each place it is read from -- the channel
+        slices of the pre-allocated concat buffers (and, for the first one, in place for the next convolution) -- so that
+        `torch.cat` never copies (ops.bias_leaky_relu_to / ops.cat_alias), and the fused LeakyReLU backward receives the two
+        gradients separately and sums them itself."""
+        w = _DENSE
+        B, _, H, W = x.shape
+        new = lambda c: torch.empty((B, c, H, W), device=x.device, dtype=torch.float32)
+        b2, b3, b4, b5 = new(w[0] + w[1]), new(w[1] + w[2]), new(w[2] + w[3]), new(w[3] + w[4])
+        conv = lambda i: getattr(self, 'conv%d_%d' % (lvl, i))
+        x0a, x0b = conv(0)(x, dsts=[(None, 0), (b2, 0)])
+        x1a, x1b = conv(1)(x0a, dsts=[(b2, w[0]), (b3, 0)])
+        x2a, x2b = conv(2)(ops.cat_alias(b2, (x0b, x1a)), dsts=[(b3, w[1]), (b4, 0)])
+        x3a, x3b = conv(3)(ops.cat_alias(b3, (x1b, x2a)), dsts=[(b4, w[2]), (b5, 0)])
+        if lvl == 2:        # x4 also feeds the context network
+            x4a, x4b = conv(4)(ops.cat_alias(b4, (x2b, x3a)), dsts=[(b5, w[3]), (None, 0)])
+        else:
+            (x4a,) = conv(4)(ops.cat_alias(b4, (x2b, x3a)), dsts=[(b5, w[3])])
+            x4b = None
+        return getattr(self, 'predict_flow%d' % lvl)(ops.cat_alias(b5, (x3b, x4a))), x4b
 
     def forward(self, feature_list_1, feature_list_2, img_hw):
         """pwc_tf.py:108-179.  The first feature list may carry 1/rep of the second one's batch: it is then taken as

@@ -645,6 +645,98 @@ def bias_leaky_relu_(y: torch.Tensor, bias: torch.Tensor, negative_slope: float 
     return _BiasLeakyReLU.apply(y, bias.contiguous(), negative_slope, bool(fork))
 
 
+class _BiasLeakyReLUTo(torch.autograd.Function):
+    """lrelu(y + bias) of a fresh convolution output, written straight to where its consumers read it: `dsts` is a list of
+    one or two `(buffer, channel_offset)` pairs (buffer = a pre-allocated (B,Ctot,H,W) concat buffer, or `None` for "in
+    place on y").  Returns one tensor per destination: the channel slice of the buffer (or y).  With `_CatAlias` this makes
+    the dense block's concatenations (pwc_tf.py:113-118) copy-free.  The buffers are not autograd inputs -- they travel in
+    a Python list -- so the returned slices are ordinary outputs of this node."""
+
+    @staticmethod
+    def forward(ctx, y, bias, slope, dsts):
+        assert y.is_contiguous() and 1 <= len(dsts) <= 2
+        B, C, H, W = y.shape
+        outs, ptrs = [], []
+        for buf, off in dsts:
+            if buf is None:
+                o = y
+            else:
+                assert buf.is_contiguous() and buf.shape[0] == B and tuple(buf.shape[2:]) == (H, W) and off + C <= buf.shape[1]
+                o = buf[:, off:off + C]
+            outs.append(o)
+            ptrs += [_p(o), o.stride(0)]
+        if len(dsts) == 1:
+            ptrs += [None, 0]
+        with torch.cuda.device_of(y):
+            _lib.call('uof_bias_lrelu_fwd2', _p(y), _p(bias), *ptrs, B, C, H, W, float(slope), _stream(y))
+        if dsts[0][0] is None or (len(dsts) == 2 and dsts[1][0] is None):
+            ctx.mark_dirty(y)
+        ctx.save_for_backward(outs[0])
+        ctx.slope = float(slope)
+        return tuple(o if o is y else o.detach() for o in outs) if len(outs) > 1 else (outs[0] if outs[0] is y else outs[0].detach())
+
+    @staticmethod
+    def backward(ctx, g1, g2=None):
+        (y,) = ctx.saved_tensors
+        B, C, H, W = y.shape
+        if g1 is None:
+            g1, g2 = g2, None
+        if g1 is None:
+            return None, None, None, None
+        if not _sample_dense(g1, C, H, W):
+            g1 = g1.contiguous()
+        if g2 is not None and not _sample_dense(g2, C, H, W):
+            g2 = g2.contiguous()
+        gx = torch.empty((B, C, H, W), device=y.device, dtype=torch.float32)
+        gbias = torch.empty(C, device=y.device, dtype=torch.float32)
+        _alert_not_deterministic('uof_bias_lrelu_bwd (bias gradient)')
+        with torch.cuda.device_of(y):
+            _lib.call('uof_bias_lrelu_bwd3', _p(g1), g1.stride(0), _p(g2) if g2 is not None else None,
+                      g2.stride(0) if g2 is not None else 0, _p(y), y.stride(0), _p(gx), _p(gbias), B, C, H, W, ctx.slope,
+                      _stream(y))
+        return gx, gbias, None, None
+
+
+def bias_leaky_relu_to(y: torch.Tensor, bias: torch.Tensor, dsts, negative_slope: float = 0.1):
+    """lrelu(y + bias[None,:,None,None]) written to one or two destinations (see _BiasLeakyReLUTo); `y` must be a freshly
+    produced contiguous NCHW convolution output.  Returns a tuple with one tensor per destination."""
+    _require_cuda(y, bias)
+    if not y.is_contiguous():
+        y = y.contiguous()
+    out = _BiasLeakyReLUTo.apply(y, bias.contiguous(), negative_slope, list(dsts))
+    return out if isinstance(out, tuple) else (out,)
+
+
+class _CatAlias(torch.autograd.Function):
+    """torch.cat(parts, 1) when the parts ALREADY are the consecutive channel slices of `buf` (written there by
+    bias_leaky_relu_to): returns `buf` itself, no copy; backward hands each part its channel slice of the gradient (views)."""
+
+    @staticmethod
+    def forward(ctx, buf_box, *parts):
+        buf = buf_box[0]
+        off = 0
+        for t in parts:
+            assert t.data_ptr() == buf.data_ptr() + off * buf.stride(1) * buf.element_size() and t.stride(0) == buf.stride(0), \
+                'cat_alias: a part is not the expected slice of the buffer'
+            off += t.shape[1]
+        assert off == buf.shape[1]
+        ctx.sizes = [t.shape[1] for t in parts]
+        return buf.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for c in ctx.sizes:
+            outs.append(g[:, off:off + c])
+            off += c
+        return (None, *outs)
+
+
+def cat_alias(buf: torch.Tensor, parts):
+    """== torch.cat(parts, 1), given that `parts` are the channel slices of `buf` in order (no copy)."""
+    return _CatAlias.apply([buf], *parts)
+
+
 class _UpsampleScaled(torch.autograd.Function):
     """scale * F.interpolate(x, size, mode='bilinear') (align_corners=False) in one kernel each way."""
 
