@@ -116,6 +116,36 @@ int uof_photo_loss_fwd(const uof_photo_level* levels, int nlevels, int B,
 int uof_photo_loss_bwd(const uof_photo_level* levels, int nlevels, int B, const float* sums,
                        const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream);
 
+/* a3+a4+a5+a6 fused (round 2): the image warps of Model_flow.forward (warp_flow_pyramid, model_flow_paper.py:62-66,
+ * 236-237 -> net_utils.py:16-54 with use_mask=True) evaluated INSIDE the photometric kernels above.  The forward kernel
+ * gathers the left / right image at (pixel + flow) itself -- same coordinate arithmetic, same validity mask, same blend
+ * order as uof_warp_fwd, so the warped values are bit-identical -- and the backward kernel turns d loss / d warped into
+ * d loss / d flow in its epilogue (uof_warp_bwd without gradient w.r.t. the image).  One launch each way for all pyramid
+ * levels and both directions instead of 3 + 1 (forward) and 1 + 3 (backward).
+ * Requires even W and 8-byte aligned planes at every level (else UOF_ERR_UNSUPPORTED: use the separate entry points). */
+typedef struct {
+  const float* img;        /* (B,3,H,W) target image at this level                                     */
+  const float* src_l;      /* (B,3,H,W) left image at this level, sampled with flow_l                  */
+  const float* src_r;      /* (B,3,H,W) right image, sampled with flow_r                               */
+  const float* flow_l;     /* (B,2,H,W) flow target -> left  (reference "bwd")                         */
+  const float* flow_r;     /* (B,2,H,W) flow target -> right (reference "fwd")                         */
+  float* warped_l;         /* (B,3,H,W) masked warp: written by fwd (NULL: not stored), read by bwd    */
+  float* warped_r;
+  float* weight_l;         /* (B,1,H,W) weight maps: written by fwd (NULL: not stored), read by bwd    */
+  float* weight_r;
+  float* diff_l;           /* (B,1,H,W) out of fwd: mean_c |img - warped|, or NULL                     */
+  float* diff_r;
+  float* gflow_l;          /* (B,2,H,W) out of bwd: d loss / d flow_l                                  */
+  float* gflow_r;
+  int H, W;
+} uof_photo_warp_level;
+/* coord_flags: bit 0 align_corners, bit 1 UOF_COORD_HOST (see uof_warp_fwd).  sums / loss_*: as uof_photo_loss_fwd. */
+int uof_photo_warp_loss_fwd(const uof_photo_warp_level* levels, int nlevels, int B, int coord_flags,
+                            float* sums, float* loss_pixel, float* loss_ssim, uof_stream_t stream);
+/* backward: needs warped_*, weight_* as written by the forward call on the same inputs; writes gflow_*. */
+int uof_photo_warp_loss_bwd(const uof_photo_warp_level* levels, int nlevels, int B, int coord_flags, const float* sums,
+                            const float* g_loss_pixel, const float* g_loss_ssim, uof_stream_t stream);
+
 /* a4 seam: Model_flow.compute_diff_weight (model_flow_paper.py:101-134) on one pyramid level.
  * img, warped_*: (B,3,H,W); diff_*, weight_*: (B,1,H,W).  Weights carry no gradient (detached in the reference). */
 int uof_diff_weight_fwd(const float* img, const float* warped_l, const float* warped_r, float* diff_l, float* diff_r,

@@ -58,6 +58,17 @@ def test_argument_validation_without_gpu(lib):
         _lib.call('uof_img_pyramid_stacked', P, 64, 192, 64, 8, P, slots, outs, 3, 3, 1, 3, 8, 8, None)
     with pytest.raises(ValueError, match='too large for one launch'):
         _lib.call('uof_splat_fwd', None, P, P, 1, 70000, 4, 1, None)
+    with pytest.raises(ValueError, match='nlevels'):
+        _lib.call('uof_photo_warp_loss_fwd', None, 0, 1, 0, P, P, P, None)
+    with pytest.raises(ValueError, match='coord_flags'):
+        _lib.call('uof_photo_warp_loss_bwd', None, 1, 1, 7, P, P, P, None)
+    lv = (_lib.PhotoWarpLevel * 1)()
+    lv[0] = _lib.PhotoWarpLevel(16, 16, 16, 16, 16, None, None, None, None, None, None, None, None, 8, 7)
+    with pytest.raises(RuntimeError, match='even W'):             # UOF_ERR_UNSUPPORTED: the caller takes the separate kernels
+        _lib.call('uof_photo_warp_loss_fwd', lv, 1, 1, 0, P, P, P, None)
+    lv[0] = _lib.PhotoWarpLevel(16, 16, 16, 16, 16, None, None, None, None, None, None, None, None, 8, 8)
+    with pytest.raises(ValueError, match='needs the warped images'):
+        _lib.call('uof_photo_warp_loss_bwd', lv, 1, 1, 0, P, P, P, None)
 
 
 def test_library_missing_fails_loudly(tmp_path, monkeypatch):

@@ -567,6 +567,162 @@ def test_photometric_fused_vs_oracle(U, B, H, W):
         assert_close(g2[s], torch.cat((got_g[s], got_g[S + s]), 0), 1e-5)
 
 
+@pytest.mark.parametrize('ac', [False, True])
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 40, 72), (2, 16, 136)])
+def test_photo_warp_fused_vs_oracle(U, B, H, W, ac):
+    """a3+a4+a5+a6 in one launch each way (uof_photo_warp_loss_*): image warps with validity mask evaluated inside the
+    photometric kernels, against the CPU oracle chain warp_flow -> diff_weight -> loss_with_mask / loss_ssim
+    (model_flow_paper.py:236-245): losses, weight / diff maps, the warped images and d loss / d flow."""
+    g = torch.Generator().manual_seed(B * 1000 + H + int(ac))
+    S = 3
+    pyr, fb, ff, _, _ = pyramid_case(g, B, H, W, S)
+    fb = [f.requires_grad_(True) for f in fb]
+    ff = [f.requires_grad_(True) for f in ff]
+    from_l = [O.warp_flow(pyr[0][s], fb[s], use_mask=True, align_corners=ac) for s in range(S)]
+    from_r = [O.warp_flow(pyr[2][s], ff[s], use_mask=True, align_corners=ac) for s in range(S)]
+    d_b, d_f, w_b, w_f = O.diff_weight(from_l, pyr[1], from_r, S)
+    ref_pix = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+    ref_ssim = O.loss_ssim(pyr[1], from_r, w_f, S) + O.loss_ssim(pyr[1], from_l, w_b, S)
+    ct = torch.randn(2, B, generator=g)
+    ref_g = torch.autograd.grad((ref_pix * ct[0]).sum() + (ref_ssim * ct[1]).sum(), fb + ff)
+
+    ci = [t.cuda() for t in pyr[1]]
+    src = [torch.cat((pyr[0][s], pyr[2][s]), 0).cuda() for s in range(S)]
+    fl = [torch.cat((fb[s], ff[s]), 0).detach().cuda().requires_grad_(True) for s in range(S)]
+    pix, ssim, gw_b, gw_f, gd_b, gd_f, warped = U.ops.photometric_losses_warped(ci, src, fl, S, ac, return_diffs=True,
+                                                                               return_warped=True)
+    got_g = torch.autograd.grad((pix * ct[0].cuda()).sum() + (ssim * ct[1].cuda()).sum(), fl)
+    assert_close(pix, ref_pix, REL_TOL, 'loss_pixel')
+    assert_close(ssim, ref_ssim, REL_TOL, 'loss_ssim')
+    for s in range(S):
+        assert_close(warped[s], torch.cat((from_l[s], from_r[s]), 0), REL_TOL, 'warped')
+        assert_close(gw_b[s], w_b[s], REL_TOL, 'weight_bwd')
+        assert_close(gw_f[s], w_f[s], REL_TOL, 'weight_fwd')
+        assert_close(gd_b[s], d_b[s], REL_TOL, 'diff_bwd')
+        assert_close(gd_f[s], d_f[s], REL_TOL, 'diff_fwd')
+        assert float(ref_g[s].abs().max()) > 0
+        assert_close(got_g[s], torch.cat((ref_g[s], ref_g[S + s]), 0), REL_TOL, 'd loss / d flow, level %d' % s)
+
+
+@pytest.mark.parametrize('ac', [False, True])
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (3, 72, 200), (8, 256, 832)])
+def test_photo_warp_fused_matches_separate_kernels(U, B, H, W, ac):
+    """The fused launch against uof_warp_fwd/bwd + uof_photo_loss_fwd/bwd on the same GPU, up to BASELINE configs[1]'s
+    shapes (B=8, 256x832, three scales): the warped images and the weight maps must be BIT-identical (same coordinate
+    chain, same blend order), losses agree to the order of the atomics, flow gradients to 1e-5."""
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(H * 7 + B + int(ac))
+    S = 3
+    r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+    imgs = [O.img_pyramid(r(B, 3, H, W), S) for _ in range(3)]
+    lo = (r(2 * B, 2, H // 8, W // 8) - 0.5) * 6.0
+    flows = [torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)
+             + (r(2 * B, 2, H >> s, W >> s) - 0.5) * 0.5 for s in range(S)]
+    for s in range(S):                       # an out-of-bounds column and row (validity mask 0)
+        flows[s][:, 0, :, (W >> s) - 2] += W >> s
+        flows[s][:, 1, 1, :] -= H >> s
+    src = [torch.cat((imgs[0][s], imgs[2][s]), 0) for s in range(S)]
+    ct = torch.randn(2, B, device=dev, generator=g)
+
+    f1 = [f.clone().requires_grad_(True) for f in flows]
+    warped1 = [U.warp_flow(src[s], f1[s], use_mask=True, align_corners=ac) for s in range(S)]
+    pix1, ssim1, wb1, wf1 = U.ops.photometric_losses_stacked(imgs[1], warped1, S)
+    g1 = torch.autograd.grad((pix1 * ct[0]).sum() + (ssim1 * ct[1]).sum(), f1)
+
+    f2 = [f.clone().requires_grad_(True) for f in flows]
+    pix2, ssim2, wb2, wf2, warped2 = U.ops.photometric_losses_warped(imgs[1], src, f2, S, ac, return_warped=True)
+    g2 = torch.autograd.grad((pix2 * ct[0]).sum() + (ssim2 * ct[1]).sum(), f2)
+    assert_close(pix2, pix1, 2e-6, 'loss_pixel')
+    assert_close(ssim2, ssim1, 2e-6, 'loss_ssim')
+    for s in range(S):
+        assert torch.equal(warped2[s], warped1[s].detach()), 'warped images differ at level %d' % s
+        assert torch.equal(wb2[s], wb1[s]) and torch.equal(wf2[s], wf1[s]), 'weight maps differ at level %d' % s
+        assert float((warped2[s] == 0).all(1).float().mean()) > 0.001          # the mask is exercised
+        assert float(g1[s].abs().max()) > 0
+        assert_close(g2[s], g1[s], 1e-5, 'd loss / d flow, level %d' % s)
+
+
+def test_photo_warp_fused_full_size_vs_same_gpu_oracle(U):
+    """BASELINE configs[1] shapes (B=8, 256x832, three scales, [bwd ; fwd] stacked): the fused warp + photometric launch
+    against the ORACLE's op chain (ATen grid_sample + the restated losses) on the same GPU.  Pixels whose in-bounds weight
+    sum lies within rounding of the 0.9999 threshold may flip between the two implementations; they must be < 0.1 % and
+    the flow gradient is compared where the masks agree."""
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(4242)
+    B, H, W, S = 8, 256, 832, 3
+    r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+    imgs = [O.img_pyramid(r(B, 3, H, W), S) for _ in range(3)]
+    lo = (r(2 * B, 2, H // 8, W // 8) - 0.5) * 6.0
+    flows = [torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)
+             + (r(2 * B, 2, H >> s, W >> s) - 0.5) * 0.5 for s in range(S)]
+    src = [torch.cat((imgs[0][s], imgs[2][s]), 0) for s in range(S)]
+    ct = torch.randn(2, B, device=dev, generator=g)
+
+    fr = [f.clone().requires_grad_(True) for f in flows]
+    wl = [O.warp_flow(imgs[0][s], fr[s][:B], use_mask=True) for s in range(S)]
+    wr = [O.warp_flow(imgs[2][s], fr[s][B:], use_mask=True) for s in range(S)]
+    d_b, d_f, w_b, w_f = O.diff_weight(wl, imgs[1], wr, S)
+    rpix = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+    rssim = O.loss_ssim(imgs[1], wr, w_f, S) + O.loss_ssim(imgs[1], wl, w_b, S)
+    rg = torch.autograd.grad((rpix * ct[0]).sum() + (rssim * ct[1]).sum(), fr)
+
+    fc = [f.clone().requires_grad_(True) for f in flows]
+    pix, ssim, wb, wf, warped = U.ops.photometric_losses_warped(imgs[1], src, fc, S, return_warped=True)
+    gg = torch.autograd.grad((pix * ct[0]).sum() + (ssim * ct[1]).sum(), fc)
+    assert_close(pix, rpix, REL_TOL, 'loss_pixel at 8x256x832')
+    assert_close(ssim, rssim, REL_TOL, 'loss_ssim at 8x256x832')
+    for s in range(S):
+        ref_w = torch.cat((wl[s], wr[s]), 0).detach()
+        agree = ((warped[s] != 0).any(1, keepdim=True) == (ref_w != 0).any(1, keepdim=True))
+        assert float(agree.float().mean()) >= MASK_AGREE
+        # a flipped validity also changes the weights of its 3x3 SSIM neighbourhood: compare away from flips
+        near = torch.nn.functional.max_pool2d((~agree).float(), 5, 1, 2) > 0
+        keep = ~near
+        assert float(keep.float().mean()) >= 0.99
+        assert_close(warped[s] * keep, ref_w * keep, REL_TOL, 'warped')
+        assert_close(gg[s] * keep, rg[s] * keep, REL_TOL, 'd loss / d flow at 8x256x832, level %d' % s)
+
+
+def test_losses_golden_from_reference_fused_warp(U):
+    """tests/golden/losses.npz (recorded from the unmodified reference) through the fused warp + photometric launch."""
+    g = load_golden('losses.npz')
+    S = 3
+    B = g['img'].shape[0]
+    pyr = [U.ops.img_pyramid(g[k].cuda(), 4) for k in ('imgl', 'img', 'imgr')]
+    fl = [torch.cat((g['fb%d' % s], g['ff%d' % s]), 0).cuda().requires_grad_(True) for s in range(S)]
+    src = [torch.cat((pyr[0][s], pyr[2][s]), 0) for s in range(S)]
+    pix, ssim, w_b, w_f = U.ops.photometric_losses_warped(pyr[1], src, fl, S)
+    smooth = U.ops.flow_smooth_loss(fl, pyr[1], S)
+    consis = U.ops.flow_consis_loss([f[B:] for f in fl], [f[:B] for f in fl], w_f, S)
+    pack = [pix, ssim, smooth[B:] + smooth[:B], consis]
+    total = sum((p * c.cuda()).sum() for p, c in zip(pack, g['cts']))
+    grads = torch.autograd.grad(total, fl)
+    for k, name in enumerate(('loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis')):
+        assert_close(pack[k], g[name], REL_TOL, name)
+    for s in range(S):
+        assert_close(w_b[s], g['wb%d' % s], REL_TOL)
+        assert_close(w_f[s], g['wf%d' % s], REL_TOL)
+        assert_close(grads[s][:B], g['gfb%d' % s], REL_TOL, 'grad flow bwd %d' % s)
+        assert_close(grads[s][B:], g['gff%d' % s], REL_TOL, 'grad flow fwd %d' % s)
+
+
+def test_photo_warp_odd_width_takes_separate_kernels(U):
+    """Levels with odd W cannot use the pixel-pair kernels: the host op falls back to uof_warp_* + uof_photo_loss_* (still
+    CUDA) and the C ABI says UOF_ERR_UNSUPPORTED rather than computing something else."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W, S = 2, 20, 27, 1
+    pyr, fb, ff, from_l, from_r = pyramid_case(g, B, H, W, S)
+    d_b, d_f, w_b, w_f = O.diff_weight(from_l, pyr[1], from_r, S)
+    ref_pix = O.loss_with_mask(d_f, w_f, S) + O.loss_with_mask(d_b, w_b, S)
+    src = [torch.cat((pyr[0][0], pyr[2][0]), 0).cuda()]
+    fl = [torch.cat((fb[0], ff[0]), 0).cuda().requires_grad_(True)]
+    pix, ssim, _, _ = U.ops.photometric_losses_warped([pyr[1][0].cuda()], src, fl, S)
+    assert_close(pix, ref_pix, REL_TOL)
+    assert torch.autograd.grad(pix.sum() + ssim.sum(), fl)[0].abs().max() > 0
+    with pytest.raises(ValueError, match='images are data'):
+        U.ops.photometric_losses_warped([pyr[1][0].cuda()], [src[0].clone().requires_grad_(True)], fl, S)
+
+
 def test_photometric_backward_kernel_variants_agree(U):
     """uof_photo_loss_bwd has three kernels: pixel-pair (weights given, even W), split (weights given, odd W somewhere)
     and fused-direction (no weight maps: recomputes them).  All must produce the same gradients through the C ABI."""

@@ -26,6 +26,16 @@ class PhotoLevel(ctypes.Structure):
                 ('H', ctypes.c_int), ('W', ctypes.c_int)]
 
 
+class PhotoWarpLevel(ctypes.Structure):
+    _fields_ = [('img', ctypes.c_void_p), ('src_l', ctypes.c_void_p), ('src_r', ctypes.c_void_p),
+                ('flow_l', ctypes.c_void_p), ('flow_r', ctypes.c_void_p),
+                ('warped_l', ctypes.c_void_p), ('warped_r', ctypes.c_void_p),
+                ('weight_l', ctypes.c_void_p), ('weight_r', ctypes.c_void_p),
+                ('diff_l', ctypes.c_void_p), ('diff_r', ctypes.c_void_p),
+                ('gflow_l', ctypes.c_void_p), ('gflow_r', ctypes.c_void_p),
+                ('H', ctypes.c_int), ('W', ctypes.c_int)]
+
+
 class SmoothLevel(ctypes.Structure):
     _fields_ = [('flow', ctypes.c_void_p), ('img', ctypes.c_void_p), ('gflow', ctypes.c_void_p),
                 ('H', ctypes.c_int), ('W', ctypes.c_int)]
@@ -48,6 +58,8 @@ SIGNATURES = {
     'uof_warp_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'uof_photo_loss_fwd': [ctypes.POINTER(PhotoLevel), _I, _I, _P, _P, _P, _P],
     'uof_photo_loss_bwd': [ctypes.POINTER(PhotoLevel), _I, _I, _P, _P, _P, _P],
+    'uof_photo_warp_loss_fwd': [ctypes.POINTER(PhotoWarpLevel), _I, _I, _I, _P, _P, _P, _P],
+    'uof_photo_warp_loss_bwd': [ctypes.POINTER(PhotoWarpLevel), _I, _I, _I, _P, _P, _P, _P],
     'uof_diff_weight_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'uof_diff_weight_bwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'uof_masked_mean_fwd': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_I),

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libuof_b200.so')
-SOURCES = ['runtime.cu', 'cost_volume.cu', 'cost_volume_tma.cu', 'cost_volume_small.cu', 'cost_volume_tc.cu', 'warp.cu', 'photo_loss.cu', 'ssim_map.cu', 'flow_losses.cu',
+SOURCES = ['runtime.cu', 'cost_volume.cu', 'cost_volume_tma.cu', 'cost_volume_small.cu', 'cost_volume_tc.cu', 'warp.cu', 'photo_loss.cu', 'photo_warp.cu', 'ssim_map.cu', 'flow_losses.cu',
            'seams.cu', 'splat.cu', 'pyramid.cu', 'act.cu', 'upsample.cu', 'io_pipeline.cu']
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 

@@ -125,6 +125,39 @@ def cases(B=8, H=256, W=832):
     yield ('photo_loss_bwd[3 scales, 2 dirs]', 60 * px,
            [lambda q=q: _lib.call('uof_photo_loss_bwd', q[2], S, B, ops._p(q[3]), ops._p(q[6]), ops._p(q[6]), ops._stream(anchor)) for q in psets])
 
+    # image warps fused into the photometric kernels (what Model_flow.forward launches): decoder-like flows, [l ; r] stacked
+    from ._lib import PhotoWarpLevel
+
+    def photo_warp_set():
+        imgs = [u(B, 3, H >> s, W >> s) for s in range(S)]
+        src = [u(B2, 3, H >> s, W >> s) for s in range(S)]
+        lo = r(B2, 2, H // 32, W // 32) * 2.5
+        fl = [(torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)).contiguous()
+              for s in range(S)]
+        wpd = [torch.empty(B2, 3, H >> s, W >> s, device=dev) for s in range(S)]
+        wl = [torch.empty(B, 1, H >> s, W >> s, device=dev) for s in range(S)]
+        wr = [torch.empty(B, 1, H >> s, W >> s, device=dev) for s in range(S)]
+        gf = [torch.empty_like(t) for t in fl]
+        lv = (PhotoWarpLevel * S)()
+        for s in range(S):
+            lv[s] = PhotoWarpLevel(imgs[s].data_ptr(), src[s][:B].data_ptr(), src[s][B:].data_ptr(), fl[s][:B].data_ptr(),
+                                   fl[s][B:].data_ptr(), wpd[s][:B].data_ptr(), wpd[s][B:].data_ptr(), wl[s].data_ptr(),
+                                   wr[s].data_ptr(), None, None, gf[s][:B].data_ptr(), gf[s][B:].data_ptr(), H >> s, W >> s)
+        sums, lp, ls = torch.zeros(S * B * 6 + _lib.SUMS_EXTRA, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev)
+        g = torch.ones(B, device=dev)
+        keep.append((imgs, src, fl, wpd, wl, wr, gf, lv, sums, lp, ls, g))
+        return lv, sums, lp, ls, g
+
+    # compulsory traffic of the fused op per target pixel: forward reads img 12 + two sources 24 + two flows 16 and writes
+    # two weight maps 8 = 60 B (the 24 B of warped values it also stores for its backward pass are not counted); backward
+    # reads img 12 + two sources 24 + two flows 16 + weights 8 and writes two flow gradients 16 = 76 B (the 24 B of saved
+    # warped values it reads are not counted)
+    wsets = [photo_warp_set() for _ in range(_nsets(84 * px))]
+    yield ('photo_warp_loss_fwd[3 scales, 2 dirs, image warps fused]', 60 * px,
+           [lambda q=q: _lib.call('uof_photo_warp_loss_fwd', q[0], S, B, 0, ops._p(q[1]), ops._p(q[2]), ops._p(q[3]), ops._stream(anchor)) for q in wsets])
+    yield ('photo_warp_loss_bwd[3 scales, 2 dirs, image warps fused]', 76 * px,
+           [lambda q=q: _lib.call('uof_photo_warp_loss_bwd', q[0], S, B, 0, ops._p(q[1]), ops._p(q[4]), ops._p(q[4]), ops._stream(anchor)) for q in wsets])
+
     def flow_set(i):
         fl = [r(B2, 2, H >> s, W >> s) for s in range(S)]
         gf = [torch.empty_like(t) for t in fl]

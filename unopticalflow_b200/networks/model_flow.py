@@ -133,10 +133,13 @@ class Model_flow(nn.Module):
             pyr_l, pyr_c, pyr_r, _ = ops.img_pyramid_triplet(inputs, S)              # one launch, triplet read in place
             sources = [torch.cat((pyr_l[s], pyr_r[s]), 0) for s in range(S)]
         flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
-        warped = [ops.warp_flow(sources[s], flows[s], use_mask=True, align_corners=self.align_corners)
-                  for s in range(S)]                                                  # [from_l ; from_r]
-
-        loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
+        if ops.FUSE_IMAGE_WARP:
+            # image warps evaluated inside the photometric kernels: one launch each way instead of 3 + 1
+            loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_warped(pyr_c, sources, flows, S, self.align_corners)
+        else:
+            warped = [ops.warp_flow(sources[s], flows[s], use_mask=True, align_corners=self.align_corners)
+                      for s in range(S)]                                              # [from_l ; from_r]
+            loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
         smooth = ops.flow_smooth_loss(flows, pyr_c, S)                               # (2B,): [bwd ; fwd]
         consis = ops.flow_consis_loss([f[B:] for f in flows[:S]], [f[:B] for f in flows[:S]], w_fwd, S)
         loss_pack = {'loss_pixel': loss_pixel, 'loss_ssim': loss_ssim,

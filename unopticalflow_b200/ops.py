@@ -10,11 +10,12 @@ on the current CUDA stream.  CPU tensors raise: there is no fallback path.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from . import _lib
-from ._lib import ConsisLevel, PhotoLevel, SmoothLevel
+from ._lib import ConsisLevel, PhotoLevel, PhotoWarpLevel, SmoothLevel
 
 # grid_sample convention of "the reference executed under the installed torch" (SURVEY F4).
 DEFAULT_ALIGN_CORNERS = False
@@ -23,6 +24,9 @@ DEFAULT_ALIGN_CORNERS = False
 # division; the arithmetic of the CPU oracle and the golden fixtures).  One ulp of the normalised coordinate apart, which at
 # W ~ 800 is 2.5e-5 px and ~1e-4 relative in the flow gradient -- as far as the reference is from itself across devices.
 COORD_ARITHMETIC = 'cuda'
+# Model_flow.forward evaluates the image warps inside the photometric kernels (uof_photo_warp_loss_*); UOF_NO_PHOTO_WARP=1
+# keeps the separate uof_warp_* + uof_photo_loss_* launches (A/B measurements, profiles/r2_photo_warp.md).
+FUSE_IMAGE_WARP = os.environ.get('UOF_NO_PHOTO_WARP') is None
 
 
 def _coord_flags(align_corners):
@@ -401,6 +405,102 @@ def photometric_losses_stacked(img_pyramid, warped_lr, num_scales=3, return_diff
     _require_cuda(*img_pyramid[:S], *warped_lr[:S])
     outs = _PhotoLoss.apply(S, bool(return_diffs), True, *img_pyramid[:S], *warped_lr[:S])
     return _unpack_photo(outs, S, return_diffs)
+
+
+# --------------------------------------------------------------------------------- a3+a4+a5+a6
+class _PhotoWarpLoss(torch.autograd.Function):
+    """Image warps fused into the photometric losses: warp_flow_pyramid x2 + compute_diff_weight + 2x compute_loss_with_mask
+    + 2x compute_loss_ssim (model_flow_paper.py:236-245) as ONE launch each way.
+
+    tensors = imgs[S] + sources[S] + flows[S]: imgs[s] (B,3,H,W) target, sources[s] (2B,3,H,W) = [left ; right] images,
+    flows[s] (2B,2,H,W) = [target->left ("bwd") ; target->right ("fwd")].  Gradient flows to the flows only (the images
+    are data).  Outputs: loss_pixel, loss_ssim, weight maps (l then r), [diff maps], masked warped images (2B,3,H,W) --
+    everything after the two losses is non-differentiable, as in the reference (weights are detached, :131-132)."""
+
+    @staticmethod
+    def forward(ctx, S, flags, want_diff, *tensors):
+        imgs = [t.contiguous() for t in tensors[:S]]
+        srcs = [t.contiguous() for t in tensors[S:2 * S]]
+        flows = [t.contiguous() for t in tensors[2 * S:3 * S]]
+        B = imgs[0].shape[0]
+        dev = imgs[0].device
+        lv = _levels(PhotoWarpLevel, S)
+        warped, weights_l, weights_r, diffs_l, diffs_r = [], [], [], [], []
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            if (tuple(imgs[s].shape) != (B, 3, H, W) or tuple(srcs[s].shape) != (2 * B, 3, H, W)
+                    or tuple(flows[s].shape) != (2 * B, 2, H, W)):
+                raise ValueError('photometric_losses_warped level %d: image %r, sources %r, flows %r must be (B,3,H,W), '
+                                 '(2B,3,H,W), (2B,2,H,W)' % (s, tuple(imgs[s].shape), tuple(srcs[s].shape), tuple(flows[s].shape)))
+            warped.append(torch.empty((2 * B, 3, H, W), device=dev, dtype=torch.float32))
+            weights_l.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+            weights_r.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+            if want_diff:
+                diffs_l.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+                diffs_r.append(torch.empty((B, 1, H, W), device=dev, dtype=torch.float32))
+            lv[s] = PhotoWarpLevel(imgs[s].data_ptr(), srcs[s][:B].data_ptr(), srcs[s][B:].data_ptr(),
+                                   flows[s][:B].data_ptr(), flows[s][B:].data_ptr(),
+                                   warped[s][:B].data_ptr(), warped[s][B:].data_ptr(),
+                                   weights_l[s].data_ptr(), weights_r[s].data_ptr(),
+                                   diffs_l[s].data_ptr() if want_diff else None, diffs_r[s].data_ptr() if want_diff else None,
+                                   None, None, H, W)
+        _alert_not_deterministic('uof_photo_warp_loss_fwd')
+        sums = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, device=dev, dtype=torch.float32)
+        loss_pixel, loss_ssim = torch.empty(B, device=dev, dtype=torch.float32), torch.empty(B, device=dev, dtype=torch.float32)
+        with torch.cuda.device_of(imgs[0]):
+            _lib.call('uof_photo_warp_loss_fwd', lv, S, B, flags, _p(sums), _p(loss_pixel), _p(loss_ssim), _stream(imgs[0]))
+        ctx.save_for_backward(sums, *imgs, *srcs, *flows, *warped, *weights_l, *weights_r)
+        ctx.S, ctx.flags = S, flags
+        outs = (loss_pixel, loss_ssim, *weights_l, *weights_r, *diffs_l, *diffs_r, *warped)
+        ctx.mark_non_differentiable(*outs[2:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pixel, g_ssim, *unused):
+        S = ctx.S
+        sums, *rest = ctx.saved_tensors
+        imgs, srcs, flows, warped = rest[:S], rest[S:2 * S], rest[2 * S:3 * S], rest[3 * S:4 * S]
+        wl, wr = rest[4 * S:5 * S], rest[5 * S:6 * S]
+        B = imgs[0].shape[0]
+        gflows = [torch.empty_like(f) for f in flows]
+        lv = _levels(PhotoWarpLevel, S)
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            lv[s] = PhotoWarpLevel(imgs[s].data_ptr(), srcs[s][:B].data_ptr(), srcs[s][B:].data_ptr(),
+                                   flows[s][:B].data_ptr(), flows[s][B:].data_ptr(),
+                                   warped[s][:B].data_ptr(), warped[s][B:].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(),
+                                   None, None, gflows[s][:B].data_ptr(), gflows[s][B:].data_ptr(), H, W)
+        g_pixel = torch.zeros(B, device=sums.device, dtype=torch.float32) if g_pixel is None else g_pixel.contiguous()
+        g_ssim = torch.zeros(B, device=sums.device, dtype=torch.float32) if g_ssim is None else g_ssim.contiguous()
+        with torch.cuda.device_of(sums):
+            _lib.call('uof_photo_warp_loss_bwd', lv, S, B, ctx.flags, _p(sums), _p(g_pixel), _p(g_ssim), _stream(sums))
+        return (None, None, None, *([None] * (2 * S)), *gflows)
+
+
+def photometric_losses_warped(img_pyramid, sources_lr, flows_lr, num_scales=3, align_corners=None, return_diffs=False,
+                              return_warped=False):
+    """`warp_flow_pyramid` (both directions, use_mask=True) + the fused photometric losses of Model_flow.forward
+    (model_flow_paper.py:236-245) without materialising the warped pyramids between two launches.
+
+    img_pyramid[s] (B,3,H,W); sources_lr[s] (2B,3,H,W) = [left ; right]; flows_lr[s] (2B,2,H,W) = [bwd ; fwd].
+    Returns (loss_pixel (B,), loss_ssim (B,), weight_bwd list, weight_fwd list[, diff_bwd, diff_fwd][, warped_lr list]).
+    Levels with odd W (the pair kernels need even W) take the separate warp + photometric kernels instead."""
+    S = num_scales
+    imgs, srcs, flows = list(img_pyramid[:S]), list(sources_lr[:S]), list(flows_lr[:S])
+    _require_cuda(*imgs, *srcs, *flows)
+    ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+    if any(t.requires_grad for t in imgs + srcs):
+        raise ValueError('photometric_losses_warped: the images are data (no gradient w.r.t. them); use warp_flow + '
+                         'photometric_losses_stacked for differentiable sources')
+    if any(int(t.shape[-1]) % 2 for t in imgs):
+        warped = [warp_flow(srcs[s], flows[s], use_mask=True, align_corners=ac) for s in range(S)]
+        res = photometric_losses_stacked(imgs, warped, S, return_diffs)
+        return res + (warped,) if return_warped else res
+    outs = _PhotoWarpLoss.apply(S, _coord_flags(ac), bool(return_diffs), *imgs, *srcs, *flows)
+    res = _unpack_photo(outs, S, return_diffs)
+    if return_warped:
+        res += (list(outs[-S:]),)
+    return res
 
 
 # ------------------------------------------------------------------------------- a4 / a5 seams
