@@ -156,6 +156,10 @@ def algorithmic_bytes(name, args):
         return 36 * lv_pixels(args[0], args[1], args[2])
     if name == 'uof_photo_loss_bwd':
         return 60 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_photo_warp_loss_fwd':       # image warps fused in: img 12 + two sources 24 + two flows 16 + two weight maps 8
+        return 60 * lv_pixels(args[0], args[1], args[2])
+    if name == 'uof_photo_warp_loss_bwd':       # img 12 + sources 24 + flows 16 + weights 8 + two flow gradients 16
+        return 76 * lv_pixels(args[0], args[1], args[2])
     if name == 'uof_smooth_loss_fwd':
         return 20 * lv_pixels(args[0], args[1], args[2])
     if name == 'uof_smooth_loss_bwd':

@@ -31,10 +31,11 @@ namespace {
 
 constexpr float kMaskThreshold = 0.9999f;   // net_utils.py:50
 constexpr int kFwdWarps = 4;                // 2 strips x 2 directions
-constexpr int kFwdDepth = 3;                // rows in the forward cp.async ring
+constexpr int kFwdDepth = 3;                // rows in the forward cp.async ring (the pipeline below assumes 3)
 constexpr int kFwdPlanes = 5;               // img x3, flow x2
 constexpr int kBwdWarps = 6;                // direction x channel
 constexpr int kBwdDepth = 4;
+constexpr int kBwdSmem = kBwdWarps * (6 * 32 * 16 + kBwdDepth * 3 * 32 * 8 + 10 * 32 * 4) + 2 * 2 * 3 * 3 * 32 * 8;
 
 struct PWParams {
   uof_photo_warp_level lv[UOF_MAX_LEVELS];
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, MINB)
 photo_warp_fwd_kernel(const __grid_constant__ PWParams P, float* __restrict__ sums) {
   pdl_trigger();      // the finalize grid is a programmatic dependent (common.cuh)
   __shared__ float2 ring_s[kFwdWarps][kFwdDepth * kFwdPlanes * 32];
+  __shared__ float4 gat_s[kFwdWarps][2][6 * 32];             // gathered corners, see below
   __shared__ float2 xch_s[kFwdWarps][2][32];                 // [warp][row parity][lane]: this warp's mean |I - W| pair
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int dir = wid & 1;                                   // 0: left / "bwd", 1: right / "fwd"
@@ -122,36 +124,58 @@ photo_warp_fwd_kernel(const __grid_constant__ PWParams P, float* __restrict__ su
       cp_async_8(d + 4 * 32, flo + plane + o, inb);
       cp_async_commit();
     };
-    const int r_begin = sc.y0 - 1, r_end = sc.y1;
-#pragma unroll
-    for (int i = 0; i < kFwdDepth - 1; ++i) fetch(r_begin + i, i);
-    int slot = 0;
-    for (int r = r_begin; r <= r_end; ++r) {
-      fetch(r + kFwdDepth - 1, slot == 0 ? kFwdDepth - 1 : slot - 1);
-      cp_async_wait<kFwdDepth - 1>();
-      f2 v[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) v[k] = ring[slot * (kFwdPlanes * 32) + k * 32];
-      const f2 fx = ring[slot * (kFwdPlanes * 32) + 3 * 32], fy = ring[slot * (kFwdPlanes * 32) + 4 * 32];
-      slot = slot + 1 == kFwdDepth ? 0 : slot + 1;
-
-      // the warp (net_utils.py:39-54): footprints of the two pixels, 24 gathers issued together, masked blend
+    // The warp (net_utils.py:39-54), software-pipelined by one row: while row r is processed, the footprints of row r+1 are
+    // formed from its flow (already in the ring) and its 4 corners x 3 channels x 2 pixels are gathered with 4-byte
+    // cp.async into a per-warp shared-memory slot; only the 8 blend weights stay in registers.  (Gathering into registers
+    // right before the blend left 27 % of the samples on long-scoreboard stalls at the first use, ncu round 2.)
+    float4* gat = gat_s[wid][0] + lane;                      // [slot][channel * 2 + pixel][lane] = 4 corners
+    float wq[8];
+    auto gather = [&](int r, int rslot, int gslot) {
+      const f2 fx = ring[rslot * (kFwdPlanes * 32) + 3 * 32], fy = ring[rslot * (kFwdPlanes * 32) + 4 * 32];
       const bool inb = pin && r >= 0 && r < H;
       const Foot f0 = make_foot<FLAGS>(px0, (float)r, fx.x, fy.x, H, W, inb);
       const Foot f1 = make_foot<FLAGS>(px1, (float)r, fx.y, fy.y, H, W, inb);
-      float g0[3][4], g1[3][4];
+      float* d = reinterpret_cast<float*>(gat + gslot * (6 * 32));
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* sp = src + c * plane;
-        g0[c][0] = __ldg(sp + f0.o00); g0[c][1] = __ldg(sp + f0.o01); g0[c][2] = __ldg(sp + f0.o10); g0[c][3] = __ldg(sp + f0.o11);
-        g1[c][0] = __ldg(sp + f1.o00); g1[c][1] = __ldg(sp + f1.o01); g1[c][2] = __ldg(sp + f1.o10); g1[c][3] = __ldg(sp + f1.o11);
+        float* d0 = d + (c * 2) * (32 * 4);
+        float* d1 = d0 + 32 * 4;
+        cp_async_4(d0, sp + f0.o00, true); cp_async_4(d0 + 1, sp + f0.o01, true);
+        cp_async_4(d0 + 2, sp + f0.o10, true); cp_async_4(d0 + 3, sp + f0.o11, true);
+        cp_async_4(d1, sp + f1.o00, true); cp_async_4(d1 + 1, sp + f1.o01, true);
+        cp_async_4(d1 + 2, sp + f1.o10, true); cp_async_4(d1 + 3, sp + f1.o11, true);
       }
-      f2 wv[3];
+      cp_async_commit();
+      wq[0] = f0.w00; wq[1] = f0.w01; wq[2] = f0.w10; wq[3] = f0.w11;
+      wq[4] = f1.w00; wq[5] = f1.w01; wq[6] = f1.w10; wq[7] = f1.w11;
+    };
+    const int r_begin = sc.y0 - 1, r_end = sc.y1;
+    fetch(r_begin, 0);
+    fetch(r_begin + 1, 1);
+    cp_async_wait<1>();
+    gather(r_begin, 0, 0);
+    int slot = 0;
+    for (int r = r_begin; r <= r_end; ++r) {
+      // groups in flight: [rows r+1] [gathers of row r] -> + [row r+2]; all but the newest must have landed
+      const int slot1 = slot + 1 == kFwdDepth ? 0 : slot + 1;
+      fetch(r + 2, slot == 0 ? kFwdDepth - 1 : slot - 1);
+      cp_async_wait<1>();
+      f2 v[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        wv[c].x = fmaf(g0[c][3], f0.w11, fmaf(g0[c][2], f0.w10, fmaf(g0[c][1], f0.w01, g0[c][0] * f0.w00)));
-        wv[c].y = fmaf(g1[c][3], f1.w11, fmaf(g1[c][2], f1.w10, fmaf(g1[c][1], f1.w01, g1[c][0] * f1.w00)));
+      for (int k = 0; k < 3; ++k) v[k] = ring[slot * (kFwdPlanes * 32) + k * 32];
+      f2 wv[3];
+      {
+        const float4* gs = gat + ((r - r_begin) & 1) * (6 * 32);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float4 a = gs[(c * 2) * 32], b = gs[(c * 2 + 1) * 32];
+          wv[c].x = fmaf(a.w, wq[3], fmaf(a.z, wq[2], fmaf(a.y, wq[1], a.x * wq[0])));
+          wv[c].y = fmaf(b.w, wq[7], fmaf(b.z, wq[6], fmaf(b.y, wq[5], b.x * wq[4])));
+        }
       }
+      if (r < r_end) gather(r + 1, slot1, (r + 1 - r_begin) & 1);
+      slot = slot1;
 
       // weights of both pixels (model_flow_paper.py:111-129): this direction's mean |I - W| and validity are local, the other
       // direction's mean difference comes from the partner warp
@@ -283,10 +307,14 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
   }
 
   const int r_begin = sc.y0 - 2, r_end = sc.y1 + 1;
-  __shared__ float2 ring_s[kBwdWarps][kBwdDepth * 3 * 32];
+  // dynamic shared memory (52.5 KB > the 48 KB static limit), carved with typed pointer arithmetic on the array itself
+  extern __shared__ float4 bwd_smem[];
+  float4* const gat_all = bwd_smem;                                                        // [warp][6 * 32] float4
+  float2* const ring_all = reinterpret_cast<float2*>(gat_all + kBwdWarps * 6 * 32);        // [warp][depth * 3 * 32] float2
   // gW hand-over: [triple parity][direction][row of the triple][channel][lane]
-  __shared__ float2 gw_s[2][2][3][3][32];
-  float2* ring = ring_s[role] + lane;
+  float2 (*gw_s)[2][3][3][32] = reinterpret_cast<float2 (*)[2][3][3][32]>(ring_all + kBwdWarps * kBwdDepth * 3 * 32);
+  float* const fsc_all = reinterpret_cast<float*>(&gw_s[2][0][0][0][0]);                   // [warp][10 * 32] float
+  float2* ring = ring_all + role * (kBwdDepth * 3 * 32) + lane;
   auto fetch = [&](int r, int slot) {
     const bool inb = pin && r >= 0 && r < H;
     const unsigned o = (unsigned)min(max(r, 0), H - 1) * W;
@@ -298,26 +326,62 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
   };
 #pragma unroll
   for (int i = 0; i < kBwdDepth - 1; ++i) fetch(r_begin + i, i);
+  // Epilogue pipeline: the flow of this warp's row of the NEXT triple is loaded one triple ahead (registers); at the top
+  // of a triple the footprints of its row are formed, the 4 corners x 3 channels x 2 pixels are gathered with cp.async
+  // (zero-filled for out-of-bounds corners) and the five scalars per pixel the flow gradient needs are parked in shared
+  // memory; the three rows of photometric work then hide the gather latency.
+  float* gat = reinterpret_cast<float*>(gat_all + role * (6 * 32) + lane);   // [channel * 2 + pixel][lane] = corners 00, 01, 10, 11
+  float* fsc = fsc_all + role * (10 * 32) + lane;                            // [pixel * 5 + {tx, ty, ux, uy, mask}][lane]
+  auto flow_of = [&](int p, float2& fx, float2& fy) {
+    fx = fy = make_float2(0.0f, 0.0f);
+    if (pout && p >= sc.y0 && p < sc.y1) {
+      fx = __ldg(reinterpret_cast<const float2*>(flo + (unsigned)p * W));
+      fy = __ldg(reinterpret_cast<const float2*>(flo + plane + (unsigned)p * W));
+    }
+  };
+  float2 fxn, fyn;
+  flow_of(r_begin + c - 2, fxn, fyn);
   int slot = 0, par = 0;
   for (int rb = r_begin; rb <= r_end; rb += 3, par ^= 1) {
-    // this warp's row of the triple: p = rb + c - 2.  Its flow is loaded now and used after the barrier.
+    // this warp's row of the triple: p = rb + c - 2
     const int pmine = rb + c - 2;
     const bool mine = pout && pmine >= sc.y0 && pmine < sc.y1;
-    float2 fxp = make_float2(0.0f, 0.0f), fyp = fxp;
     if (mine) {
-      fxp = __ldg(reinterpret_cast<const float2*>(flo + (unsigned)pmine * W));
-      fyp = __ldg(reinterpret_cast<const float2*>(flo + plane + (unsigned)pmine * W));
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float ix = sample_coord((float)(sc.col + k), k ? fxn.y : fxn.x, W, FLAGS);
+        const float iy = sample_coord((float)pmine, k ? fyn.y : fyn.x, H, FLAGS);
+        const Bilinear bl = make_bilinear(ix, iy, H, W);
+        const float cover = ((bl.w00 + bl.w01) + bl.w10) + bl.w11;
+        const int xa = min(max(bl.x0, 0), W - 1), xb = min(max(bl.x0 + 1, 0), W - 1);
+        const int ya = min(max(bl.y0, 0), H - 1) * W, yb = min(max(bl.y0 + 1, 0), H - 1) * W;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const float* sp = src + cc * plane;
+          float* d = gat + (cc * 2 + k) * (32 * 4);
+          cp_async_4(d, sp + ya + xa, bl.in00);
+          cp_async_4(d + 1, sp + ya + xb, bl.in01);
+          cp_async_4(d + 2, sp + yb + xa, bl.in10);
+          cp_async_4(d + 3, sp + yb + xb, bl.in11);
+        }
+        fsc[(k * 5 + 0) * 32] = bl.tx;
+        fsc[(k * 5 + 1) * 32] = bl.ty;
+        fsc[(k * 5 + 2) * 32] = (floorf(ix) + 1.0f) - ix;
+        fsc[(k * 5 + 3) * 32] = (floorf(iy) + 1.0f) - iy;
+        fsc[(k * 5 + 4) * 32] = cover < kMaskThreshold ? 0.0f : 1.0f;
+      }
     }
+    cp_async_commit();                 // every warp commits the same number of groups per triple (see the wait below)
+    flow_of(pmine + 3, fxn, fyn);
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
       const int r = rb + u;
       f2 gw = splat2(0.0f);
+      fetch(r + kBwdDepth - 1, slot == 0 ? kBwdDepth - 1 : slot - 1);     // also past r_end: keeps the group count uniform
       if (r <= r_end) {
         // ring slots of the moments: row r -> u, q = r-1 -> (u+2)%3, p = r-2 -> (u+1)%3
-        fetch(r + kBwdDepth - 1, slot == 0 ? kBwdDepth - 1 : slot - 1);
         cp_async_wait<kBwdDepth - 1>();
         const float2 vI = ring[slot * 96], vW = ring[slot * 96 + 32], vw = ring[slot * 96 + 64];
-        slot = slot + 1 == kBwdDepth ? 0 : slot + 1;
         const float d0 = vI.x - vW.x, d1 = vI.y - vW.y;
         wl1[u][0] = vw;
         // d(masked L1)/dW = -sign(I-W) w coef
@@ -355,45 +419,34 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
           gw = fma2(gy, wl1[sp][0], wl1[sp][1]);           // d loss / d warped_c at (p, pair)
         }
       }
+      slot = slot + 1 == kBwdDepth ? 0 : slot + 1;
       gw_s[par][dir][u][c][lane] = gw;
     }
     __syncwarp();
     named_barrier<96>(dir);      // the three channel warps of this direction have left their gW of rows rb-2 .. rb
+    cp_async_wait<3>();              // the three row groups of this triple may still be in flight, the gathers have landed
     if (mine) {
       // warp_flow backward for row pmine, all three channels (warp.cu:warp_bwd_nchw_kernel, NEED_GX = false)
-      // one pixel at a time (not unrolled): the epilogue runs once per three rows and must not inflate the register
-      // allocation of the row loop
-      float* go = gfl + (unsigned)pmine * W;
-#pragma unroll 1
-      for (int k = 0; k < 2; ++k) {
-        const float fxk = k ? fxp.y : fxp.x, fyk = k ? fyp.y : fyp.x;
-        const float ix = sample_coord((float)(sc.col + k), fxk, W, FLAGS);
-        const float iy = sample_coord((float)pmine, fyk, H, FLAGS);
-        const Bilinear bl = make_bilinear(ix, iy, H, W);
-        const float cover = ((bl.w00 + bl.w01) + bl.w10) + bl.w11;
-        const float msk = cover < kMaskThreshold ? 0.0f : 1.0f;
-        const int xa = min(max(bl.x0, 0), W - 1), xb = min(max(bl.x0 + 1, 0), W - 1);
-        const int ya = min(max(bl.y0, 0), H - 1) * W, yb = min(max(bl.y0 + 1, 0), H - 1) * W;
-        const float ux = (floorf(ix) + 1.0f) - ix, uy = (floorf(iy) + 1.0f) - iy;
-        float v[3][4];
+      float gx2[2], gy2[2];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const float* sp = src + cc * plane;
-          v[cc][0] = __ldg(sp + ya + xa); v[cc][1] = __ldg(sp + ya + xb); v[cc][2] = __ldg(sp + yb + xa); v[cc][3] = __ldg(sp + yb + xb);
-        }
+      for (int k = 0; k < 2; ++k) {
+        const float tx = fsc[(k * 5 + 0) * 32], ty = fsc[(k * 5 + 1) * 32], ux = fsc[(k * 5 + 2) * 32], uy = fsc[(k * 5 + 3) * 32];
+        const float msk = fsc[(k * 5 + 4) * 32];
         float gix = 0.0f, giy = 0.0f;
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
+          const float4 v = *reinterpret_cast<const float4*>(gat + (cc * 2 + k) * (32 * 4));     // 00, 01, 10, 11
           const float2 g2 = gw_s[par][dir][c][cc][lane];
           const float gm = (k ? g2.y : g2.x) * msk;
-          const float v00 = bl.in00 ? v[cc][0] : 0.0f, v01 = bl.in01 ? v[cc][1] : 0.0f;
-          const float v10 = bl.in10 ? v[cc][2] : 0.0f, v11 = bl.in11 ? v[cc][3] : 0.0f;
-          gix = fmaf(gm, (v01 - v00) * uy + (v11 - v10) * bl.ty, gix);
-          giy = fmaf(gm, (v10 - v00) * ux + (v11 - v01) * bl.tx, giy);
+          gix = fmaf(gm, (v.y - v.x) * uy + (v.w - v.z) * ty, gix);
+          giy = fmaf(gm, (v.z - v.x) * ux + (v.w - v.y) * tx, giy);
         }
-        go[k] = gix * sx;
-        go[plane + k] = giy * sy;
+        gx2[k] = gix * sx;
+        gy2[k] = giy * sy;
       }
+      float* go = gfl + (unsigned)pmine * W;
+      *reinterpret_cast<float2*>(go) = make_float2(gx2[0], gx2[1]);
+      *reinterpret_cast<float2*>(go + plane) = make_float2(gy2[0], gy2[1]);
     }
   }
   cp_async_wait<0>();
@@ -453,18 +506,30 @@ int launch_fwd(PWParams& P, const uof_photo_warp_level* levels, int nlevels, int
   return UOF_OK;
 }
 
+// opt in to > 48 KB of dynamic shared memory (once per instantiation) and return the resident blocks per SM
+template <class K>
+int bwd_occupancy(K kernel) {
+  int n = 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBwdWarps * 32, kBwdSmem) != cudaSuccess || n < 1) {
+    (void)cudaGetLastError();
+    n = 2;
+  }
+  return n;
+}
+
 template <int MINB>
 int launch_bwd(PWParams& P, const uof_photo_warp_level* levels, int nlevels, int B, int flags, const float* sums, const float* gp,
                const float* gs, cudaStream_t stream) {
-  static const int occ[4] = {resident_blocks(photo_warp_bwd_kernel<0, MINB>, kBwdWarps * 32), resident_blocks(photo_warp_bwd_kernel<1, MINB>, kBwdWarps * 32),
-                             resident_blocks(photo_warp_bwd_kernel<2, MINB>, kBwdWarps * 32), resident_blocks(photo_warp_bwd_kernel<3, MINB>, kBwdWarps * 32)};
+  static const int occ[4] = {bwd_occupancy(photo_warp_bwd_kernel<0, MINB>), bwd_occupancy(photo_warp_bwd_kernel<1, MINB>),
+                             bwd_occupancy(photo_warp_bwd_kernel<2, MINB>), bwd_occupancy(photo_warp_bwd_kernel<3, MINB>)};
   if (int rc = fill_params(P, levels, nlevels, B, true, occ[flags])) return rc;
   const int blocks = P.T.warp_begin[nlevels];
   switch (flags) {
-    case 0: photo_warp_bwd_kernel<0, MINB><<<blocks, kBwdWarps * 32, 0, stream>>>(P, sums, gp, gs); break;
-    case 1: photo_warp_bwd_kernel<1, MINB><<<blocks, kBwdWarps * 32, 0, stream>>>(P, sums, gp, gs); break;
-    case 2: photo_warp_bwd_kernel<2, MINB><<<blocks, kBwdWarps * 32, 0, stream>>>(P, sums, gp, gs); break;
-    default: photo_warp_bwd_kernel<3, MINB><<<blocks, kBwdWarps * 32, 0, stream>>>(P, sums, gp, gs); break;
+    case 0: photo_warp_bwd_kernel<0, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    case 1: photo_warp_bwd_kernel<1, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    case 2: photo_warp_bwd_kernel<2, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    default: photo_warp_bwd_kernel<3, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
   }
   return UOF_OK;
 }
