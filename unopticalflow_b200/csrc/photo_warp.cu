@@ -263,7 +263,7 @@ __global__ void photo_warp_finalize_kernel(const __grid_constant__ PWParams P, c
 // epilogue: instead of storing gW = d loss / d warped, the channel warps hand it over in shared memory and the flow
 // gradient is formed here (warp.cu:warp_bwd_nchw_kernel without the scatter to the image).
 template <int FLAGS, int MINB>
-__global__ void __launch_bounds__(kBwdWarps * 32, MINB)
+__global__ void __launch_bounds__(kBwdWarps * 32) __maxnreg__(MINB == 3 ? 112 : (MINB == 2 ? 168 : 255))
 photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restrict__ sums,
                       const float* __restrict__ g_pixel, const float* __restrict__ g_ssim) {
   const int lane = threadIdx.x & 31;
@@ -347,8 +347,8 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
     const int pmine = rb + c - 2;
     const bool mine = pout && pmine >= sc.y0 && pmine < sc.y1;
     if (mine) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
+#pragma unroll 1
+      for (int k = 0; k < 2; ++k) {       // not unrolled: 12 instead of 24 64-bit gather addresses live on top of the row state
         const float ix = sample_coord((float)(sc.col + k), k ? fxn.y : fxn.x, W, FLAGS);
         const float iy = sample_coord((float)pmine, k ? fyn.y : fyn.x, H, FLAGS);
         const Bilinear bl = make_bilinear(ix, iy, H, W);
