@@ -107,10 +107,13 @@ def test_conv_block_fused_bias_lrelu(U, cin, cout, h, w, stride, dil):
 
 
 @pytest.mark.parametrize('shape,size,scale', [((2, 2, 4, 13), (8, 26), 2.0), ((3, 2, 16, 52), (64, 208), 4.0),
-                                              ((1, 3, 5, 7), (11, 20), 1.0), ((2, 2, 6, 6), (6, 6), 4.0)])
+                                              ((1, 3, 5, 7), (11, 20), 1.0), ((2, 2, 6, 6), (6, 6), 4.0),
+                                              ((2, 2, 64, 208), (256, 832), 4.0), ((2, 2, 37, 150), (74, 300), 2.0),
+                                              ((1, 2, 9, 130), (36, 520), 4.0), ((1, 1, 1, 1), (4, 4), 4.0), ((1, 1, 1, 3), (2, 6), 2.0)])
 def test_upsample_bilinear_scaled(U, shape, size, scale):
     """Fused `F.interpolate(x, size, mode='bilinear') * scale` (pwc_tf.py:119,174-177) against ATen on the same GPU: values
-    and the gather-form gradient (ATen scatters with atomics), integer and non-integer ratios, identity size."""
+    and the gather-form gradient (ATen scatters with atomics); exact x2 / x4 ratios (the specialised register-window kernels:
+    multi-block rows, odd heights, one-pixel inputs), non-integer ratios and the identity size (generic kernels)."""
     g = torch.Generator().manual_seed(sum(shape))
     x = torch.randn(shape, generator=g).cuda()
     ct = torch.randn(shape[0], shape[1], *size, generator=g).cuda()
@@ -122,7 +125,7 @@ def test_upsample_bilinear_scaled(U, shape, size, scale):
     ga, = torch.autograd.grad((ya * ct).sum(), [xa])
     gb, = torch.autograd.grad((yb * ct).sum(), [xb])
     assert_close(ga, gb, 1e-5, 'upsample bwd')
-    if scale == 2.0:     # the decoder's form: scale_factor=2.0, multiplied afterwards
+    if scale == 2.0 and size[0] == 2 * shape[2]:     # the decoder's form: scale_factor=2.0, multiplied afterwards
         yc = torch.nn.functional.interpolate(x, scale_factor=2.0, mode='bilinear') * 2.0
         assert_close(ya, yc, 1e-6, 'x2 up-sampling vs the reference expression')
 
