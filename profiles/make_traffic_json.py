@@ -16,6 +16,8 @@ from collections import defaultdict
 
 MAIN = {'cost_volume_fwd': 'uof_cost_volume_fwd', 'cost_volume_bwd': 'uof_cost_volume_bwd', 'warp_fwd': 'uof_warp_fwd',
         'warp_bwd': 'uof_warp_bwd', 'photo_loss_fwd_kernel': 'uof_photo_loss_fwd', 'photo_loss_bwd': 'uof_photo_loss_bwd',
+        'photo_warp_fwd': 'uof_photo_warp_loss_fwd', 'photo_warp_bwd': 'uof_photo_warp_loss_bwd',
+        'upsample_fwd': 'uof_upsample_bilinear_fwd', 'upsample_bwd': 'uof_upsample_bilinear_bwd',
         'smooth_fwd': 'uof_smooth_loss_fwd', 'smooth_bwd': 'uof_smooth_loss_bwd', 'consis_fwd': 'uof_consis_loss_fwd',
         'consis_bwd': 'uof_consis_loss_bwd', 'pyramid': 'uof_img_pyramid', 'ssim_fwd': 'uof_ssim_fwd', 'ssim_bwd': 'uof_ssim_bwd',
         'splat': 'uof_splat_fwd', 'bias_lrelu_fwd': 'uof_bias_lrelu_fwd', 'bias_lrelu_bwd': 'uof_bias_lrelu_bwd'}      # bench.py keys uof_bias_lrelu_bwd2 calls as uof_bias_lrelu_bwd[...]

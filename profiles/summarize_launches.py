@@ -6,7 +6,7 @@ import sys
 from collections import defaultdict
 
 
-OWN = re.compile(r'cost_volume_|warp_(fwd|bwd)_n|photo_loss_|smooth_(fwd|bwd|finalize)|consis_(fwd|bwd|finalize)|pyramid_|ssim_(fwd|bwd)_kernel|'
+OWN = re.compile(r'cost_volume_|warp_(fwd|bwd)_n|photo_loss_|photo_warp_|upsample_(fwd|bwd)(_int)?_kernel|smooth_(fwd|bwd|finalize)|consis_(fwd|bwd|finalize)|pyramid_|ssim_(fwd|bwd)_kernel|'
                  r'splat|fb_mask|clamp01|diff_weight_|masked_mean_|bias_lrelu_')
 
 
