@@ -235,18 +235,19 @@ def test_cost_volume_ex_strided_operand_and_folded_gradient(U, shape):
     assert_close(g2, r2, REL_TOL, 'corr bwd_ex grad f2')
 
 
-def test_cost_volume_small_backward_opt_in():
-    """cost_volume_small.cu's backward kernel is opt-in (slower than the tiled kernels, see the note at bwd_small) but stays
-    parity green: re-run the cost-volume tests (every shape; the small ones take the kernel) in a subprocess with UOF_CV_SMALL_BWD=1."""
+def test_cost_volume_small_backward_variants():
+    """The smallest levels take the shared-memory-staged backward kernel of cost_volume_small.cu by default; re-run the
+    cost-volume tests in subprocesses with it switched off (tiled kernels everywhere) and with the quad limit raised so that
+    the banded form (several row bands per image, 16x52) runs too."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, UOF_CV_SMALL_BWD='1')
     sel = 'test_cost_volume_ex_strided_operand_and_folded_gradient or test_cost_volume_vs_oracle'
-    r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', os.path.abspath(__file__), '-k',
-                        sel], env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert ' passed' in r.stdout
+    for extra in ({'UOF_CV_NO_SMALL_BWD': '1'}, {'UOF_CV_BWD_SMALL_MAXQ': '4096'}):
+        r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', os.path.abspath(__file__), '-k', sel],
+                           env=dict(os.environ, **extra), capture_output=True, text=True)
+        assert r.returncode == 0, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
+        assert ' passed' in r.stdout
 
 
 @pytest.mark.parametrize('shape,rep', [((4, 32, 16, 24), 2), ((2, 128, 8, 26), 1), ((4, 96, 16, 52), 2), ((2, 64, 32, 104), 2),
