@@ -184,6 +184,10 @@ int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, int B, int 
                         float* sums /* (nlevels,B,2) + UOF_SUMS_EXTRA */, float* loss /* (B) */, uof_stream_t stream);
 int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
                         const float* g_loss, uof_stream_t stream);
+/* same, `accumulate` != 0: gflow += (the buffer already holds another loss's gradient w.r.t. the same flows, e.g. the one
+ * written by uof_photo_warp_loss_bwd) -- saves autograd's add kernels when several losses read one flow pyramid. */
+int uof_smooth_loss_bwd_acc(const uof_smooth_level* levels, int nlevels, int B, int Bimg,
+                            const float* g_loss, int accumulate, uof_stream_t stream);
 
 /* a8: flow-direction consistency.  Replaces get_flow_normalization + compute_loss_flow_consis
  * (model_flow_paper.py:44-51,180-195).  Gradient flows to flow_fwd only. */
@@ -198,6 +202,8 @@ int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, int B,
                         float* sums /* (nlevels,B,2) + UOF_SUMS_EXTRA */, float* loss /* (B) */, uof_stream_t stream);
 int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, const float* sums,
                         const float* g_loss, uof_stream_t stream);
+int uof_consis_loss_bwd_acc(const uof_consis_level* levels, int nlevels, int B, const float* sums,
+                            const float* g_loss, int accumulate, uof_stream_t stream);
 
 /* a9: image pyramid.  Replaces Model_flow.generate_img_pyramid (model_flow_paper.py:54-60) for
  * levels 1..nlevels-1 (level 0 is the input itself); adaptive_avg_pool2d bin rule

@@ -687,6 +687,52 @@ def test_photo_warp_fused_full_size_vs_same_gpu_oracle(U):
         assert_close(gg[s] * keep, rg[s] * keep, REL_TOL, 'd loss / d flow at 8x256x832, level %d' % s)
 
 
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 40, 54), (8, 256, 832)])
+def test_flow_loss_pack_matches_separate_nodes(U, B, H, W):
+    """ops.flow_loss_pack (one autograd node: the backward kernels accumulate the three flow gradients into one buffer,
+    uof_smooth_loss_bwd_acc / uof_consis_loss_bwd_acc) against the three separate nodes whose gradients autograd sums, up to
+    BASELINE configs[1]'s shapes; (1, 40, 54) has an odd-width level and takes the composed fallback."""
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(H * 3 + B)
+    S = 3
+    r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+    imgs = [O.img_pyramid(r(B, 3, H, W), S) for _ in range(3)]
+    lo = (r(2 * B, 2, max(H // 8, 2), max(W // 8, 2)) - 0.5) * 6.0
+    flows = [torch.nn.functional.interpolate(lo, size=(H >> s, W >> s), mode='bilinear', align_corners=False) / (1 << s)
+             + (r(2 * B, 2, H >> s, W >> s) - 0.5) * 0.5 for s in range(S)]
+    src = [torch.cat((imgs[0][s], imgs[2][s]), 0) for s in range(S)]
+    ct = torch.randn(4, 2 * B, device=dev, generator=g)
+
+    def total(pix, ssim, smooth, consis):
+        return (pix * ct[0, :B]).sum() + (ssim * ct[1, :B]).sum() + (smooth * ct[2]).sum() * 100.0 + (consis * ct[3, :B]).sum()
+
+    f1 = [f.clone().requires_grad_(True) for f in flows]
+    pix1, ssim1, wb1, wf1 = U.ops.photometric_losses_warped(imgs[1], src, f1, S)
+    smooth1 = U.ops.flow_smooth_loss(f1, imgs[1], S)
+    consis1 = U.ops.flow_consis_loss([f[B:] for f in f1], [f[:B] for f in f1], wf1, S)
+    g1 = torch.autograd.grad(total(pix1, ssim1, smooth1, consis1), f1)
+
+    f2 = [f.clone().requires_grad_(True) for f in flows]
+    pix2, ssim2, smooth2, consis2, wb2, wf2 = U.ops.flow_loss_pack(imgs[1], src, f2, S)
+    g2 = torch.autograd.grad(total(pix2, ssim2, smooth2, consis2), f2)
+    for a, b, name in ((pix2, pix1, 'pixel'), (ssim2, ssim1, 'ssim'), (smooth2, smooth1, 'smooth'), (consis2, consis1, 'consis')):
+        assert a.shape == b.shape
+        assert_close(a, b, 2e-6, 'loss_' + name)
+    for s in range(S):
+        assert torch.equal(wf2[s], wf1[s]) and torch.equal(wb2[s], wb1[s])
+        assert float(g1[s].abs().max()) > 0
+        assert_close(g2[s], g1[s], 1e-5, 'd loss pack / d flow, level %d' % s)
+    # a loss that takes no part in the objective leaves its backward kernel out
+    f3 = [f.clone().requires_grad_(True) for f in flows]
+    pix3, ssim3, smooth3, consis3, _, _ = U.ops.flow_loss_pack(imgs[1], src, f3, S)
+    g3 = torch.autograd.grad((pix3 * ct[0, :B]).sum() + (ssim3 * ct[1, :B]).sum(), f3)
+    f4 = [f.clone().requires_grad_(True) for f in flows]
+    pix4, ssim4, _, _ = U.ops.photometric_losses_warped(imgs[1], src, f4, S)
+    g4 = torch.autograd.grad((pix4 * ct[0, :B]).sum() + (ssim4 * ct[1, :B]).sum(), f4)
+    for s in range(S):
+        assert_close(g3[s], g4[s], 1e-5, 'photometric-only gradient, level %d' % s)
+
+
 def test_losses_golden_from_reference_fused_warp(U):
     """tests/golden/losses.npz (recorded from the unmodified reference) through the fused warp + photometric launch."""
     g = load_golden('losses.npz')

@@ -70,6 +70,8 @@ SIGNATURES = {
     'uof_ssim_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'uof_smooth_loss_fwd': [ctypes.POINTER(SmoothLevel), _I, _I, _I, _P, _P, _P],
     'uof_smooth_loss_bwd': [ctypes.POINTER(SmoothLevel), _I, _I, _I, _P, _P],
+    'uof_smooth_loss_bwd_acc': [ctypes.POINTER(SmoothLevel), _I, _I, _I, _P, _I, _P],
+    'uof_consis_loss_bwd_acc': [ctypes.POINTER(ConsisLevel), _I, _I, _P, _P, _I, _P],
     'uof_consis_loss_fwd': [ctypes.POINTER(ConsisLevel), _I, _I, _P, _P, _P],
     'uof_consis_loss_bwd': [ctypes.POINTER(ConsisLevel), _I, _I, _P, _P, _P],
     'uof_bias_lrelu_fwd': [_P, _P, _I, _I, _I, _I, _F, _P],

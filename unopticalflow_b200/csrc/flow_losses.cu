@@ -21,6 +21,7 @@ struct SmoothParams {
   uof_smooth_level lv[UOF_MAX_LEVELS];
   StripTable T;
   int Bimg;
+  int accumulate;      // backward: gflow += instead of gflow = (the *_bwd_acc entry points)
 };
 
 __device__ void smooth_finalize(const SmoothParams& P, const float* sums, float* loss);
@@ -224,7 +225,10 @@ smooth_bwd_kernel(const __grid_constant__ SmoothParams P, const float* __restric
     if (p >= sc.y0 && p < sc.y1 && col_out) {
       const size_t o = (size_t)p * W + sc.col;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) gb[o + k * plane] = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) * 0.05f;
+      for (int k = 0; k < 2; ++k) {
+        const float v = (gxr[0][k] + (sy[0][k] - 2.0f * sy[1][k] + sy[2][k])) * 0.05f;
+        gb[o + k * plane] = P.accumulate ? gb[o + k * plane] + v : v;
+      }
     }
   }
   cp_async_wait<0>();
@@ -461,6 +465,10 @@ smooth_bwd_quad_kernel(const __grid_constant__ SmoothParams P, const float* __re
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             vp[j] = (gx[(u + 1) % 3][j][k] + (sy[(u + 1) % 3][j][k] - 2.0f * sy[(u + 2) % 3][j][k] + sy[u][j][k])) * 0.05f;
+          if (P.accumulate) {
+            const float4 t = *reinterpret_cast<const float4*>(gb + o + k * plane);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
           *reinterpret_cast<float4*>(gb + o + k * plane) = v;
         }
       }
@@ -507,6 +515,7 @@ struct ConsisParams {
   int nlevels, B;
   int vec4;          // every plane is a multiple of 4 pixels and every pointer 16-byte aligned
   int px_per_warp;   // pixels owned by a warp: kConsisPxPerWarp (backward) or kConsisFwdChunks times that (forward)
+  int accumulate;    // backward: gflow_fwd += instead of =
 };
 constexpr int kConsisPxPerWarp = 32 * 8;
 constexpr int kConsisFwdChunks = 1;      // measured: 4 chunks per warp (4x fewer blocks, barriers, REDs) is not faster (19.0 vs 18.5 us)
@@ -645,11 +654,17 @@ consis_bwd_kernel(const __grid_constant__ ConsisParams P, const float* __restric
       gy[v] = fmaf(-k, ay[it][v], uy * ia);
     }
     if (VEC == 4) {
-      *reinterpret_cast<float4*>(gf + p) = make_float4(gx[0], gx[1], gx[2], gx[3]);
-      *reinterpret_cast<float4*>(gf + plane + p) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+      float4 vx = make_float4(gx[0], gx[1], gx[2], gx[3]), vy = make_float4(gy[0], gy[1], gy[2], gy[3]);
+      if (P.accumulate) {
+        const float4 tx = *reinterpret_cast<const float4*>(gf + p), ty = *reinterpret_cast<const float4*>(gf + plane + p);
+        vx.x += tx.x; vx.y += tx.y; vx.z += tx.z; vx.w += tx.w;
+        vy.x += ty.x; vy.y += ty.y; vy.z += ty.z; vy.w += ty.w;
+      }
+      *reinterpret_cast<float4*>(gf + p) = vx;
+      *reinterpret_cast<float4*>(gf + plane + p) = vy;
     } else {
-      gf[p] = gx[0];
-      gf[plane + p] = gy[0];
+      gf[p] = P.accumulate ? gf[p] + gx[0] : gx[0];
+      gf[plane + p] = P.accumulate ? gf[plane + p] + gy[0] : gy[0];
     }
   }
 }
@@ -692,6 +707,7 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
                                    uof_stream_t stream_) {
   UOF_REQUIRE(sums && loss, "smooth_loss_fwd: null output");
   SmoothParams P;
+  P.accumulate = 0;
   static const int occ = resident_blocks(smooth_fwd_kernel, kWarpsPerBlock * 32);
   static const int occ_quad = resident_blocks(smooth_fwd_quad_kernel, kWarpsPerBlock * 32);
   const bool quad = smooth_quad_ok(levels, nlevels, false);
@@ -708,8 +724,14 @@ extern "C" int uof_smooth_loss_fwd(const uof_smooth_level* levels, int nlevels, 
 
 extern "C" int uof_smooth_loss_bwd(const uof_smooth_level* levels, int nlevels, int B, int Bimg, const float* g_loss,
                                    uof_stream_t stream_) {
+  return uof_smooth_loss_bwd_acc(levels, nlevels, B, Bimg, g_loss, 0, stream_);
+}
+
+extern "C" int uof_smooth_loss_bwd_acc(const uof_smooth_level* levels, int nlevels, int B, int Bimg, const float* g_loss,
+                                       int accumulate, uof_stream_t stream_) {
   UOF_REQUIRE(g_loss, "smooth_loss_bwd: null input");
   SmoothParams P;
+  P.accumulate = accumulate ? 1 : 0;
   static const int occ = resident_blocks(smooth_bwd_kernel, kWarpsPerBlock * 32);
   static const int occ_quad = resident_blocks(smooth_bwd_quad_kernel, kWarpsPerBlock * 32);
   const bool quad = smooth_quad_ok(levels, nlevels, true);
@@ -728,6 +750,7 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
                                    uof_stream_t stream_) {
   UOF_REQUIRE(sums && loss, "consis_loss_fwd: null output");
   ConsisParams P;
+  P.accumulate = 0;
   if (int rc = fill_consis(P, levels, nlevels, B, false)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UOF_CUDA(cudaMemsetAsync(sums, 0, ((size_t)nlevels * B * 2 + UOF_SUMS_EXTRA) * sizeof(float), stream));
@@ -742,8 +765,14 @@ extern "C" int uof_consis_loss_fwd(const uof_consis_level* levels, int nlevels, 
 
 extern "C" int uof_consis_loss_bwd(const uof_consis_level* levels, int nlevels, int B, const float* sums,
                                    const float* g_loss, uof_stream_t stream_) {
+  return uof_consis_loss_bwd_acc(levels, nlevels, B, sums, g_loss, 0, stream_);
+}
+
+extern "C" int uof_consis_loss_bwd_acc(const uof_consis_level* levels, int nlevels, int B, const float* sums,
+                                       const float* g_loss, int accumulate, uof_stream_t stream_) {
   UOF_REQUIRE(sums && g_loss, "consis_loss_bwd: null input");
   ConsisParams P;
+  P.accumulate = accumulate ? 1 : 0;
   if (int rc = fill_consis(P, levels, nlevels, B, true)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (P.vec4)

@@ -117,9 +117,11 @@ class Model_flow(nn.Module):
             # one launch: every pyramid level (level 0 as a dense copy) stacked as [left; right; centre], so the encoder's
             # 3B batch and the [left; right] warp sources are views -- no torch.cat of the images anywhere
             feats = self.fpyramid(stacked[0].view(3 * B, 3, H, W))                   # one 3B encoder pass
-            parts = [f.split(B, 0) for f in feats]                                   # (left, right, centre)
-            f1 = [c for _, _, c in parts]                                            # centre, paired with both (PWC_tf.forward repeats it)
-            f2 = [torch.cat((l, r), 0) for l, r, _ in parts]                         # [left   ; right ]
+            # [left ; right] is the leading 2B block of the stacked batch and the centre features the trailing B: two views
+            # (no concatenation forward, one concatenation of the two gradients backward)
+            parts = [ops.split_at(f, 2 * B) for f in feats]
+            f1 = [c for _, c in parts]                                               # centre, paired with both (PWC_tf.forward repeats it)
+            f2 = [lr for lr, _ in parts]                                             # [left   ; right ]
             pyr_c = [t[2] for t in stacked]
             sources = [t[:2].reshape(2 * B, 3, t.shape[3], t.shape[4]) for t in stacked]
         else:
@@ -134,14 +136,15 @@ class Model_flow(nn.Module):
             sources = [torch.cat((pyr_l[s], pyr_r[s]), 0) for s in range(S)]
         flows = self.pwc_model(f1, f2, [H, W])                                       # (2B,2,h,w): [bwd ; fwd]
         if ops.FUSE_IMAGE_WARP:
-            # image warps evaluated inside the photometric kernels: one launch each way instead of 3 + 1
-            loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_warped(pyr_c, sources, flows, S, self.align_corners)
+            # one autograd node for the four losses: image warps evaluated inside the photometric kernels (one launch each
+            # way instead of 3 + 1) and the three flow gradients accumulated into one buffer by the backward kernels
+            loss_pixel, loss_ssim, smooth, consis, w_bwd, w_fwd = ops.flow_loss_pack(pyr_c, sources, flows, S, self.align_corners)
         else:
             warped = [ops.warp_flow(sources[s], flows[s], use_mask=True, align_corners=self.align_corners)
                       for s in range(S)]                                              # [from_l ; from_r]
             loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
-        smooth = ops.flow_smooth_loss(flows, pyr_c, S)                               # (2B,): [bwd ; fwd]
-        consis = ops.flow_consis_loss([f[B:] for f in flows[:S]], [f[:B] for f in flows[:S]], w_fwd, S)
+            smooth = ops.flow_smooth_loss(flows, pyr_c, S)                           # (2B,): [bwd ; fwd]
+            consis = ops.flow_consis_loss([f[B:] for f in flows[:S]], [f[:B] for f in flows[:S]], w_fwd, S)
         loss_pack = {'loss_pixel': loss_pixel, 'loss_ssim': loss_ssim,
                      'loss_flow_smooth': smooth[B:] + smooth[:B], 'loss_flow_consis': consis}
         if output_flow:

@@ -503,6 +503,112 @@ def photometric_losses_warped(img_pyramid, sources_lr, flows_lr, num_scales=3, a
     return res
 
 
+class _FlowLossPack(torch.autograd.Function):
+    """All four losses of Model_flow.forward (model_flow_paper.py:236-251) as ONE autograd node: the fused warp +
+    photometric launch, the smoothness of both directions and the consistency loss read the same flow pyramid, and with
+    three separate nodes autograd sums their three flow gradients with ATen kernels (per level: a zero-filled full-size
+    tensor + a copy for the consistency loss's [B:] slice and two adds -- 12 launches, ~0.1 ms per step).  Here the
+    backward pass runs the three backward kernels into ONE gradient buffer per level: uof_photo_warp_loss_bwd writes it,
+    uof_smooth_loss_bwd_acc and uof_consis_loss_bwd_acc add to it in place.
+
+    tensors = imgs[S] + sources[S] + flows[S] as in _PhotoWarpLoss.  Outputs: loss_pixel (B), loss_ssim (B),
+    loss_smooth (2B) = [bwd ; fwd], loss_consis (B), then the weight maps (l then r; non-differentiable)."""
+
+    @staticmethod
+    def forward(ctx, S, flags, *tensors):
+        imgs = [t.contiguous() for t in tensors[:S]]
+        srcs = [t.contiguous() for t in tensors[S:2 * S]]
+        flows = [t.contiguous() for t in tensors[2 * S:3 * S]]
+        B = imgs[0].shape[0]
+        dev = imgs[0].device
+        f32 = dict(device=dev, dtype=torch.float32)
+        pl, sl, cl = _levels(PhotoWarpLevel, S), _levels(SmoothLevel, S), _levels(ConsisLevel, S)
+        warped, wl, wr = [], [], []
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            if (tuple(imgs[s].shape) != (B, 3, H, W) or tuple(srcs[s].shape) != (2 * B, 3, H, W)
+                    or tuple(flows[s].shape) != (2 * B, 2, H, W)):
+                raise ValueError('flow_loss_pack level %d: image %r, sources %r, flows %r must be (B,3,H,W), (2B,3,H,W), '
+                                 '(2B,2,H,W)' % (s, tuple(imgs[s].shape), tuple(srcs[s].shape), tuple(flows[s].shape)))
+            warped.append(torch.empty((2 * B, 3, H, W), **f32))
+            wl.append(torch.empty((B, 1, H, W), **f32))
+            wr.append(torch.empty((B, 1, H, W), **f32))
+            pl[s] = PhotoWarpLevel(imgs[s].data_ptr(), srcs[s][:B].data_ptr(), srcs[s][B:].data_ptr(),
+                                   flows[s][:B].data_ptr(), flows[s][B:].data_ptr(), warped[s][:B].data_ptr(),
+                                   warped[s][B:].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), None, None, None, None, H, W)
+            sl[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), None, H, W)
+            cl[s] = ConsisLevel(flows[s][B:].data_ptr(), flows[s][:B].data_ptr(), wr[s].data_ptr(), None, H, W)
+        _alert_not_deterministic('uof_photo_warp_loss_fwd / uof_smooth_loss_fwd / uof_consis_loss_fwd')
+        psums = torch.empty(S * B * 6 + _lib.SUMS_EXTRA, **f32)
+        ssums = torch.empty(S * 2 * B * 2 + _lib.SUMS_EXTRA, **f32)
+        csums = torch.empty(S * B * 2 + _lib.SUMS_EXTRA, **f32)
+        loss_pixel, loss_ssim, consis = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
+        smooth = torch.empty(2 * B, **f32)
+        st = _stream(imgs[0])
+        with torch.cuda.device_of(imgs[0]):
+            _lib.call('uof_photo_warp_loss_fwd', pl, S, B, flags, _p(psums), _p(loss_pixel), _p(loss_ssim), st)
+            _lib.call('uof_smooth_loss_fwd', sl, S, 2 * B, B, _p(ssums), _p(smooth), st)
+            _lib.call('uof_consis_loss_fwd', cl, S, B, _p(csums), _p(consis), st)
+        ctx.save_for_backward(psums, csums, *imgs, *srcs, *flows, *warped, *wl, *wr)
+        ctx.S, ctx.flags = S, flags
+        outs = (loss_pixel, loss_ssim, smooth, consis, *wl, *wr)
+        ctx.mark_non_differentiable(*outs[4:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pixel, g_ssim, g_smooth, g_consis, *unused):
+        S = ctx.S
+        psums, csums, *rest = ctx.saved_tensors
+        imgs, srcs, flows, warped = rest[:S], rest[S:2 * S], rest[2 * S:3 * S], rest[3 * S:4 * S]
+        wl, wr = rest[4 * S:5 * S], rest[5 * S:6 * S]
+        B = imgs[0].shape[0]
+        dev = psums.device
+        gflows = [torch.empty_like(f) for f in flows]
+        pl, sl, cl = _levels(PhotoWarpLevel, S), _levels(SmoothLevel, S), _levels(ConsisLevel, S)
+        for s in range(S):
+            _, _, H, W = imgs[s].shape
+            pl[s] = PhotoWarpLevel(imgs[s].data_ptr(), srcs[s][:B].data_ptr(), srcs[s][B:].data_ptr(),
+                                   flows[s][:B].data_ptr(), flows[s][B:].data_ptr(), warped[s][:B].data_ptr(),
+                                   warped[s][B:].data_ptr(), wl[s].data_ptr(), wr[s].data_ptr(), None, None,
+                                   gflows[s][:B].data_ptr(), gflows[s][B:].data_ptr(), H, W)
+            sl[s] = SmoothLevel(flows[s].data_ptr(), imgs[s].data_ptr(), gflows[s].data_ptr(), H, W)
+            cl[s] = ConsisLevel(flows[s][B:].data_ptr(), flows[s][:B].data_ptr(), wr[s].data_ptr(), gflows[s][B:].data_ptr(), H, W)
+        zeros = lambda n: torch.zeros(n, device=dev, dtype=torch.float32)
+        g_pixel = zeros(B) if g_pixel is None else g_pixel.contiguous()
+        g_ssim = zeros(B) if g_ssim is None else g_ssim.contiguous()
+        st = _stream(psums)
+        with torch.cuda.device_of(psums):
+            # the photometric kernel WRITES every element of the gradient buffers; the other two add to them
+            _lib.call('uof_photo_warp_loss_bwd', pl, S, B, ctx.flags, _p(psums), _p(g_pixel), _p(g_ssim), st)
+            if g_smooth is not None:
+                _lib.call('uof_smooth_loss_bwd_acc', sl, S, 2 * B, B, _p(g_smooth.contiguous()), 1, st)
+            if g_consis is not None:
+                _lib.call('uof_consis_loss_bwd_acc', cl, S, B, _p(csums), _p(g_consis.contiguous()), 1, st)
+        return (None, None, *([None] * (2 * S)), *gflows)
+
+
+def flow_loss_pack(img_pyramid, sources_lr, flows_lr, num_scales=3, align_corners=None):
+    """The loss pack of Model_flow.forward (model_flow_paper.py:236-251) from the image pyramids and the stacked flows, as
+    one autograd node (see _FlowLossPack).  img_pyramid[s] (B,3,H,W); sources_lr[s] (2B,3,H,W) = [left ; right];
+    flows_lr[s] (2B,2,H,W) = [bwd ; fwd].  Returns (loss_pixel (B,), loss_ssim (B,), loss_flow_smooth (2B,) = [bwd ; fwd],
+    loss_flow_consis (B,), weight_bwd list, weight_fwd list).  Needs even W at every level (else compose
+    photometric_losses_warped + flow_smooth_loss + flow_consis_loss, which is what this node computes)."""
+    S = num_scales
+    imgs, srcs, flows = list(img_pyramid[:S]), list(sources_lr[:S]), list(flows_lr[:S])
+    _require_cuda(*imgs, *srcs, *flows)
+    ac = DEFAULT_ALIGN_CORNERS if align_corners is None else bool(align_corners)
+    if any(t.requires_grad for t in imgs + srcs):
+        raise ValueError('flow_loss_pack: the images are data (no gradient w.r.t. them)')
+    B = imgs[0].shape[0]
+    if any(int(t.shape[-1]) % 2 for t in imgs):
+        pix, ssim, w_b, w_f = photometric_losses_warped(imgs, srcs, flows, S, ac)
+        smooth = flow_smooth_loss(flows, imgs, S)
+        consis = flow_consis_loss([f[B:] for f in flows], [f[:B] for f in flows], w_f, S)
+        return pix, ssim, smooth, consis, w_b, w_f
+    outs = _FlowLossPack.apply(S, _coord_flags(ac), *imgs, *srcs, *flows)
+    return outs[0], outs[1], outs[2], outs[3], list(outs[4:4 + S]), list(outs[4 + S:4 + 2 * S])
+
+
 # ------------------------------------------------------------------------------- a4 / a5 seams
 class _DiffWeight(torch.autograd.Function):
     """One level of compute_diff_weight: -> diff_l, diff_r (differentiable), weight_l, weight_r (detached)."""
@@ -835,6 +941,33 @@ class _CatAlias(torch.autograd.Function):
 def cat_alias(buf: torch.Tensor, parts):
     """== torch.cat(parts, 1), given that `parts` are the channel slices of `buf` in order (no copy)."""
     return _CatAlias.apply([buf], *parts)
+
+
+class _SplitAt(torch.autograd.Function):
+    """x -> (x[:n], x[n:]) as views; the backward pass is ONE concatenation of the two gradients.  (`torch.split` + `torch.cat`
+    of two of three parts costs a copy forward; two plain slices cost two zero-filled full-size tensors and an add backward.)"""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n, ctx.shape = n, tuple(x.shape)
+        return x[:n], x[n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        n, shape = ctx.n, ctx.shape
+        if ga is None and gb is None:
+            return None, None
+        ref = ga if ga is not None else gb
+        if ga is None:
+            ga = ref.new_zeros((n,) + shape[1:])
+        if gb is None:
+            gb = ref.new_zeros((shape[0] - n,) + shape[1:])
+        return torch.cat((ga, gb), 0), None
+
+
+def split_at(x: torch.Tensor, n: int):
+    """(x[:n], x[n:]) along the batch, both views of `x` (do not modify them in place)."""
+    return _SplitAt.apply(x, int(n))
 
 
 class _UpsampleScaled(torch.autograd.Function):
