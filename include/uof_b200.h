@@ -165,6 +165,14 @@ int uof_masked_mean_bwd(const float* const* diff, const float* const* mask, floa
                         const int* W, int nlevels, int B, int C, const float* sums, const float* g_loss,
                         uof_stream_t stream);
 
+/* Objective of the training step (train.py:147-150): out[0] = sum_k weights[k] * mean(terms[k][0..n[k])).
+ * terms / g_terms, weights, n: HOST arrays of K <= 8 entries (terms[k] device pointers); out, g_out: device scalars.
+ * Backward: g_terms[k][i] = g_out[0] * weights[k] / n[k]. */
+int uof_weighted_mean_sum_fwd(const float* const* terms, const float* weights, const int* n, int K, float* out,
+                              uof_stream_t stream);
+int uof_weighted_mean_sum_bwd(const float* g_out, const float* weights, const int* n, int K, float* const* g_terms,
+                              uof_stream_t stream);
+
 /* a6 seam: SSIM map.  Replaces SSIM(x,y) (pytorch_ssim/ssim.py:4-19) on N = B*C planes. */
 int uof_ssim_fwd(const float* x, const float* y, float* out, int N, int H, int W, uof_stream_t stream);
 int uof_ssim_bwd(const float* gout, const float* x, const float* y, float* gx, float* gy,

@@ -704,17 +704,18 @@ def test_flow_loss_pack_matches_separate_nodes(U, B, H, W):
     ct = torch.randn(4, 2 * B, device=dev, generator=g)
 
     def total(pix, ssim, smooth, consis):
-        return (pix * ct[0, :B]).sum() + (ssim * ct[1, :B]).sum() + (smooth * ct[2]).sum() * 100.0 + (consis * ct[3, :B]).sum()
+        return (pix * ct[0, :B]).sum() + (ssim * ct[1, :B]).sum() + (smooth * ct[2, :B]).sum() * 100.0 + (consis * ct[3, :B]).sum()
 
     f1 = [f.clone().requires_grad_(True) for f in flows]
     pix1, ssim1, wb1, wf1 = U.ops.photometric_losses_warped(imgs[1], src, f1, S)
     smooth1 = U.ops.flow_smooth_loss(f1, imgs[1], S)
     consis1 = U.ops.flow_consis_loss([f[B:] for f in f1], [f[:B] for f in f1], wf1, S)
-    g1 = torch.autograd.grad(total(pix1, ssim1, smooth1, consis1), f1)
+    g1 = torch.autograd.grad(total(pix1, ssim1, smooth1[B:] + smooth1[:B], consis1), f1)
 
     f2 = [f.clone().requires_grad_(True) for f in flows]
     pix2, ssim2, smooth2, consis2, wb2, wf2 = U.ops.flow_loss_pack(imgs[1], src, f2, S)
     g2 = torch.autograd.grad(total(pix2, ssim2, smooth2, consis2), f2)
+    smooth1 = smooth1[B:] + smooth1[:B]
     for a, b, name in ((pix2, pix1, 'pixel'), (ssim2, ssim1, 'ssim'), (smooth2, smooth1, 'smooth'), (consis2, consis1, 'consis')):
         assert a.shape == b.shape
         assert_close(a, b, 2e-6, 'loss_' + name)
@@ -731,6 +732,25 @@ def test_flow_loss_pack_matches_separate_nodes(U, B, H, W):
     g4 = torch.autograd.grad((pix4 * ct[0, :B]).sum() + (ssim4 * ct[1, :B]).sum(), f4)
     for s in range(S):
         assert_close(g3[s], g4[s], 1e-5, 'photometric-only gradient, level %d' % s)
+
+
+def test_weighted_mean_sum_objective(U):
+    """train.py:147-150 as one launch each way (ops.weighted_mean_sum) against the torch expression, values and gradients."""
+    g = torch.Generator().manual_seed(3)
+    terms = [torch.randn(n, generator=g).cuda().requires_grad_(True) for n in (8, 8, 16, 3)]
+    w = [0.15, 0.85, 10.0, 0.01]
+    ref_in = [t.detach().clone().requires_grad_(True) for t in terms]
+    ref = torch.stack([wk * t.mean() for wk, t in zip(w, ref_in)]).sum()
+    got = U.ops.weighted_mean_sum(terms, w)
+    assert got.shape == ref.shape == ()
+    assert_close(got, ref, 1e-6)
+    gg = torch.autograd.grad(got * 3.0, terms)
+    gr = torch.autograd.grad(ref * 3.0, ref_in)
+    for a, b in zip(gg, gr):
+        assert_close(a, b, 1e-6)
+    from unopticalflow_b200 import train
+    pack = {'a': terms[0], 'b': terms[1]}
+    assert_close(train.total_loss(pack, {'a': 2.0, 'b': 0.5}), 2.0 * terms[0].mean() + 0.5 * terms[1].mean(), 1e-6)
 
 
 def test_losses_golden_from_reference_fused_warp(U):

@@ -66,6 +66,8 @@ SIGNATURES = {
                             ctypes.POINTER(_I), _I, _I, _I, _P, _P, _P],
     'uof_masked_mean_bwd': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                             ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _I, _I, _P, _P, _P],
+    'uof_weighted_mean_sum_fwd': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_F), ctypes.POINTER(_I), _I, _P, _P],
+    'uof_weighted_mean_sum_bwd': [_P, ctypes.POINTER(_F), ctypes.POINTER(_I), _I, ctypes.POINTER(ctypes.c_void_p), _P],
     'uof_ssim_fwd': [_P, _P, _P, _I, _I, _I, _P],
     'uof_ssim_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'uof_smooth_loss_fwd': [ctypes.POINTER(SmoothLevel), _I, _I, _I, _P, _P, _P],

@@ -172,6 +172,54 @@ int fill_masked(MaskedParams& P, const float* const* diff, const float* const* m
   return UOF_OK;
 }
 
+// ---- objective of the training step (train.py:147-150): loss = sum_k w_k * mean_B(loss_k) -------------------------------
+// One block; replaces 4 means + 4 multiplies + a stack + a sum forward and their ~16 element-wise backward launches
+// (each ~2 us inside the CUDA graph) by one launch each way.
+constexpr int kMaxTerms = 8;
+struct CombineParams {
+  const float* src[kMaxTerms];
+  float* dst[kMaxTerms];
+  float w[kMaxTerms];
+  int n[kMaxTerms];
+  int K;
+};
+
+__global__ void __launch_bounds__(128) weighted_mean_sum_fwd_kernel(const __grid_constant__ CombineParams P, float* __restrict__ out) {
+  __shared__ float part[4];
+  float total = 0.0f;
+  for (int k = 0; k < P.K; ++k) {
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < P.n[k]; i += blockDim.x) s += __ldg(P.src[k] + i);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) total = fmaf(P.w[k], (part[0] + part[1] + part[2] + part[3]) / (float)P.n[k], total);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = total;
+}
+
+__global__ void __launch_bounds__(128) weighted_mean_sum_bwd_kernel(const __grid_constant__ CombineParams P, const float* __restrict__ g) {
+  const float gv = __ldg(g);
+  for (int k = 0; k < P.K; ++k) {
+    const float v = gv * P.w[k] / (float)P.n[k];
+    for (int i = threadIdx.x; i < P.n[k]; i += blockDim.x) P.dst[k][i] = v;
+  }
+}
+
+int fill_combine(CombineParams& P, const float* const* src, float* const* dst, const float* w, const int* n, int K) {
+  UOF_REQUIRE(w && n && K >= 1 && K <= kMaxTerms, "weighted_mean_sum: 1..%d terms", kMaxTerms);
+  P.K = K;
+  for (int k = 0; k < K; ++k) {
+    UOF_REQUIRE(n[k] > 0 && (src ? src[k] != nullptr : dst[k] != nullptr), "weighted_mean_sum: term %d incomplete", k);
+    P.src[k] = src ? src[k] : nullptr;
+    P.dst[k] = dst ? dst[k] : nullptr;
+    P.w[k] = w[k];
+    P.n[k] = n[k];
+  }
+  return UOF_OK;
+}
+
 }  // namespace
 }  // namespace uof
 
@@ -222,4 +270,24 @@ extern "C" int uof_masked_mean_bwd(const float* const* diff, const float* const*
   masked_mean_bwd_kernel<<<ceil_div(P.warp_begin[nlevels], 4), 128, 0, static_cast<cudaStream_t>(stream_)>>>(P, sums, g_loss);
   count_launch();
   return check_launch("masked_mean_bwd");
+}
+
+extern "C" int uof_weighted_mean_sum_fwd(const float* const* terms, const float* weights, const int* n, int K, float* out,
+                                         uof_stream_t stream_) {
+  UOF_REQUIRE(terms && out, "weighted_mean_sum_fwd: null pointer");
+  CombineParams P;
+  if (int rc = fill_combine(P, terms, nullptr, weights, n, K)) return rc;
+  weighted_mean_sum_fwd_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream_)>>>(P, out);
+  count_launch();
+  return check_launch("weighted_mean_sum_fwd");
+}
+
+extern "C" int uof_weighted_mean_sum_bwd(const float* g_out, const float* weights, const int* n, int K, float* const* g_terms,
+                                         uof_stream_t stream_) {
+  UOF_REQUIRE(g_out && g_terms, "weighted_mean_sum_bwd: null pointer");
+  CombineParams P;
+  if (int rc = fill_combine(P, nullptr, g_terms, weights, n, K)) return rc;
+  weighted_mean_sum_bwd_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream_)>>>(P, g_out);
+  count_launch();
+  return check_launch("weighted_mean_sum_bwd");
 }

@@ -143,10 +143,10 @@ class Model_flow(nn.Module):
             warped = [ops.warp_flow(sources[s], flows[s], use_mask=True, align_corners=self.align_corners)
                       for s in range(S)]                                              # [from_l ; from_r]
             loss_pixel, loss_ssim, w_bwd, w_fwd = ops.photometric_losses_stacked(pyr_c, warped, S)
-            smooth = ops.flow_smooth_loss(flows, pyr_c, S)                           # (2B,): [bwd ; fwd]
+            smooth2 = ops.flow_smooth_loss(flows, pyr_c, S)                          # (2B,): [bwd ; fwd]
+            smooth = smooth2[B:] + smooth2[:B]
             consis = ops.flow_consis_loss([f[B:] for f in flows[:S]], [f[:B] for f in flows[:S]], w_fwd, S)
-        loss_pack = {'loss_pixel': loss_pixel, 'loss_ssim': loss_ssim,
-                     'loss_flow_smooth': smooth[B:] + smooth[:B], 'loss_flow_consis': consis}
+        loss_pack = {'loss_pixel': loss_pixel, 'loss_ssim': loss_ssim, 'loss_flow_smooth': smooth, 'loss_flow_consis': consis}
         if output_flow:
             return loss_pack, [f[B:] for f in flows], [f[:B] for f in flows]
         return loss_pack

@@ -512,7 +512,8 @@ class _FlowLossPack(torch.autograd.Function):
     uof_smooth_loss_bwd_acc and uof_consis_loss_bwd_acc add to it in place.
 
     tensors = imgs[S] + sources[S] + flows[S] as in _PhotoWarpLoss.  Outputs: loss_pixel (B), loss_ssim (B),
-    loss_smooth (2B) = [bwd ; fwd], loss_consis (B), then the weight maps (l then r; non-differentiable)."""
+    loss_smooth (B) = forward-flow term + backward-flow term, loss_consis (B), then the weight maps (l then r;
+    non-differentiable)."""
 
     @staticmethod
     def forward(ctx, S, flags, *tensors):
@@ -551,7 +552,8 @@ class _FlowLossPack(torch.autograd.Function):
             _lib.call('uof_consis_loss_fwd', cl, S, B, _p(csums), _p(consis), st)
         ctx.save_for_backward(psums, csums, *imgs, *srcs, *flows, *warped, *wl, *wr)
         ctx.S, ctx.flags = S, flags
-        outs = (loss_pixel, loss_ssim, smooth, consis, *wl, *wr)
+        # model_flow_paper.py:248-249: the smoothness of the forward flow plus that of the backward flow
+        outs = (loss_pixel, loss_ssim, smooth[B:] + smooth[:B], consis, *wl, *wr)
         ctx.mark_non_differentiable(*outs[4:])
         return outs
 
@@ -581,7 +583,7 @@ class _FlowLossPack(torch.autograd.Function):
             # the photometric kernel WRITES every element of the gradient buffers; the other two add to them
             _lib.call('uof_photo_warp_loss_bwd', pl, S, B, ctx.flags, _p(psums), _p(g_pixel), _p(g_ssim), st)
             if g_smooth is not None:
-                _lib.call('uof_smooth_loss_bwd_acc', sl, S, 2 * B, B, _p(g_smooth.contiguous()), 1, st)
+                _lib.call('uof_smooth_loss_bwd_acc', sl, S, 2 * B, B, _p(g_smooth.repeat(2)), 1, st)     # both directions get g
             if g_consis is not None:
                 _lib.call('uof_consis_loss_bwd_acc', cl, S, B, _p(csums), _p(g_consis.contiguous()), 1, st)
         return (None, None, *([None] * (2 * S)), *gflows)
@@ -590,8 +592,8 @@ class _FlowLossPack(torch.autograd.Function):
 def flow_loss_pack(img_pyramid, sources_lr, flows_lr, num_scales=3, align_corners=None):
     """The loss pack of Model_flow.forward (model_flow_paper.py:236-251) from the image pyramids and the stacked flows, as
     one autograd node (see _FlowLossPack).  img_pyramid[s] (B,3,H,W); sources_lr[s] (2B,3,H,W) = [left ; right];
-    flows_lr[s] (2B,2,H,W) = [bwd ; fwd].  Returns (loss_pixel (B,), loss_ssim (B,), loss_flow_smooth (2B,) = [bwd ; fwd],
-    loss_flow_consis (B,), weight_bwd list, weight_fwd list).  Needs even W at every level (else compose
+    flows_lr[s] (2B,2,H,W) = [bwd ; fwd].  Returns (loss_pixel (B,), loss_ssim (B,), loss_flow_smooth (B,) = forward + backward
+    flow term, loss_flow_consis (B,), weight_bwd list, weight_fwd list).  Needs even W at every level (else compose
     photometric_losses_warped + flow_smooth_loss + flow_consis_loss, which is what this node computes)."""
     S = num_scales
     imgs, srcs, flows = list(img_pyramid[:S]), list(sources_lr[:S]), list(flows_lr[:S])
@@ -604,7 +606,7 @@ def flow_loss_pack(img_pyramid, sources_lr, flows_lr, num_scales=3, align_corner
         pix, ssim, w_b, w_f = photometric_losses_warped(imgs, srcs, flows, S, ac)
         smooth = flow_smooth_loss(flows, imgs, S)
         consis = flow_consis_loss([f[B:] for f in flows], [f[:B] for f in flows], w_f, S)
-        return pix, ssim, smooth, consis, w_b, w_f
+        return pix, ssim, smooth[B:] + smooth[:B], consis, w_b, w_f
     outs = _FlowLossPack.apply(S, _coord_flags(ac), *imgs, *srcs, *flows)
     return outs[0], outs[1], outs[2], outs[3], list(outs[4:4 + S]), list(outs[4 + S:4 + 2 * S])
 
@@ -941,6 +943,45 @@ class _CatAlias(torch.autograd.Function):
 def cat_alias(buf: torch.Tensor, parts):
     """== torch.cat(parts, 1), given that `parts` are the channel slices of `buf` in order (no copy)."""
     return _CatAlias.apply([buf], *parts)
+
+
+class _WeightedMeanSum(torch.autograd.Function):
+    """sum_k w_k * mean(t_k): the objective of train.py:147-150 in one launch each way."""
+
+    @staticmethod
+    def forward(ctx, weights, *terms):
+        ts = [t.contiguous() for t in terms]
+        K = len(ts)
+        ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in ts])
+        w = (ctypes.c_float * K)(*[float(v) for v in weights])
+        n = (ctypes.c_int * K)(*[t.numel() for t in ts])
+        out = torch.empty((), device=ts[0].device, dtype=torch.float32)
+        with torch.cuda.device_of(ts[0]):
+            _lib.call('uof_weighted_mean_sum_fwd', ptrs, w, n, K, _p(out), _stream(ts[0]))
+        ctx.meta = (tuple(float(v) for v in weights), tuple(tuple(t.shape) for t in ts))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        weights, shapes = ctx.meta
+        K = len(shapes)
+        g = g.contiguous()
+        outs = [torch.empty(sh, device=g.device, dtype=torch.float32) for sh in shapes]
+        ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in outs])
+        w = (ctypes.c_float * K)(*weights)
+        n = (ctypes.c_int * K)(*[t.numel() for t in outs])
+        with torch.cuda.device_of(g):
+            _lib.call('uof_weighted_mean_sum_bwd', _p(g), w, n, K, ptrs, _stream(g))
+        return (None, *outs)
+
+
+def weighted_mean_sum(terms, weights) -> torch.Tensor:
+    """sum_k weights[k] * terms[k].mean() as a 0-d tensor (train.py:147-150: the weighted batch means of the loss pack)."""
+    terms = list(terms)
+    _require_cuda(*terms)
+    if len(terms) != len(weights) or not 1 <= len(terms) <= 8:
+        raise ValueError('weighted_mean_sum: need 1..8 terms and as many weights')
+    return _WeightedMeanSum.apply(tuple(weights), *terms)
 
 
 class _SplitAt(torch.autograd.Function):

@@ -10,6 +10,8 @@ from types import SimpleNamespace
 
 import torch
 
+from . import ops
+
 KITTI_CFG = SimpleNamespace(mode='flow', dataset='kitti_depth', num_scales=3, h_flow_consist_alpha=3.0,
                             h_flow_consist_beta=0.05, w_ssim=0.85, w_flow_smooth=10.0, w_flow_consis=0.01,
                             img_hw=(256, 832), lr=1e-4, batch_size=8)          # config/kitti.yaml:11-38, train.py:168,170
@@ -26,7 +28,10 @@ def generate_loss_weights_dict(cfg):
 
 def total_loss(loss_pack, weights):
     """train.py:147-150: sum_k w_k * mean_B(loss_k)."""
-    return torch.stack([weights[k] * loss_pack[k].mean() for k in loss_pack]).sum()
+    keys = list(loss_pack)
+    if all(loss_pack[k].is_cuda and loss_pack[k].dtype == torch.float32 for k in keys):
+        return ops.weighted_mean_sum([loss_pack[k] for k in keys], [float(weights[k]) for k in keys])     # one launch each way
+    return torch.stack([weights[k] * loss_pack[k].mean() for k in keys]).sum()
 
 
 def trainable_parameters(model):
