@@ -1038,7 +1038,7 @@ def test_splat_targets_bit_exact_and_range_map(U, B, H, W, sigma):
     assert_close(occ, r_ref.clamp(0, 1), REL_TOL)
 
 
-@pytest.mark.parametrize('C', [1, 3, 8])
+@pytest.mark.parametrize('C', [1, 3, 8, 64, 160, 33])
 def test_splat_values_and_grads(U, C):
     g = torch.Generator().manual_seed(40 + C)
     B, H, W = 2, 12, 17

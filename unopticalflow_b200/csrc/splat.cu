@@ -9,6 +9,8 @@
 // corners of lane i+1 whenever the flow is locally smooth, so a lane first takes over its left
 // neighbour's right-hand contributions (shuffle + index compare) and the neighbour skips its
 // atomics -- this halves the RED traffic on smooth flows.  C % 4 == 0 uses 16-byte vector REDs.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace uof {
@@ -82,31 +84,70 @@ splat1_fwd_kernel(const float* __restrict__ u, const float2* __restrict__ flow, 
 }
 
 // ------------------------------------------------------------------------------- general C fwd
+// NHWC values with C channels (C % 4 == 0: float4 groups and 16-byte vector REDs).  grid = (chunks of W * CG threads, H, B),
+// thread = (pixel x, channel group cg) with cg fastest, so a warp touches contiguous channels of neighbouring pixels;
+// targets are 32-bit offsets inside the image.  Same warp aggregation as the C == 1 kernel: the thread CG lanes to the
+// left owns the same channel group of pixel x - 1, and when its right-hand column is this thread's left-hand column the
+// two contributions are added in registers and it skips its two REDs (needs CG < 32).  The first version decoded a
+// 64-bit linear index with three div/mod pairs and issued all four REDs per thread.
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
-splat_fwd_kernel(const float* __restrict__ u, const float2* __restrict__ flow, float* __restrict__ out, int B, int H, int W, int C) {
-  const int CG = VEC4 ? C / 4 : C;
-  const long long n = (long long)B * H * W * CG;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int cg = (int)(t % CG);
-  const long long pix = t / CG;
-  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-  const float2 f = __ldg(flow + pix);
-  const SplatGeom g = splat_geom(f.x, f.y, b, y, x, H, W);
-  if (VEC4) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(u) + pix * CG + cg);
-    float4* o = reinterpret_cast<float4*>(out);
-    auto put = [&](long long idx, float w) {
-      if (idx >= 0) atomicAdd(o + idx * CG + cg, make_float4(v.x * w, v.y * w, v.z * w, v.w * w));
-    };
-    put(g.ia, g.wa); put(g.ib, g.wb); put(g.ic, g.wc); put(g.id, g.wd);
-  } else {
-    const float v = __ldg(u + pix * CG + cg);
-    auto put = [&](long long idx, float w) {
-      if (idx >= 0) atomicAdd(out + idx * CG + cg, v * w);
-    };
-    put(g.ia, g.wa); put(g.ib, g.wb); put(g.ic, g.wc); put(g.id, g.wd);
+splat_fwd_kernel(const float* __restrict__ u, const float2* __restrict__ flow, float* __restrict__ out, int H, int W, int C,
+                 int CG) {
+  typedef typename std::conditional<VEC4, float4, float>::type V;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, lane = threadIdx.x & 31;
+  const size_t base = (size_t)blockIdx.z * H * W;          // pixels before this image
+  const unsigned x = t / (unsigned)CG, cg = t - x * (unsigned)CG;
+  const bool live = x < (unsigned)W;
+  int ia = -1, ib = -1, ic = -1, id = -1;
+  float v[4] = {0.f, 0.f, 0.f, 0.f}, wa = 0.f, wb = 0.f, wc = 0.f, wd = 0.f;
+  if (live) {
+    const size_t pix = base + (size_t)y * W + x;
+    const float2 f = __ldg(flow + pix);
+    const SplatGeom g = splat_geom(f.x, f.y, 0, y, (int)x, H, W);      // b = 0: targets relative to the image
+    ia = (int)g.ia; ib = (int)g.ib; ic = (int)g.ic; id = (int)g.id;
+    wa = g.wa; wb = g.wb; wc = g.wc; wd = g.wd;
+    if (VEC4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(u) + pix * CG + cg);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = __ldg(u + pix * CG + cg);
+    }
+  }
+  constexpr int NV = VEC4 ? 4 : 1;
+  float ca[NV], cb[NV], cc[NV], cd[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ca[k] = v[k] * wa; cb[k] = v[k] * wb; cc[k] = v[k] * wc; cd[k] = v[k] * wd;
+  }
+  bool take = false, taken = false;
+  if (CG < 32) {             // uniform
+    const int nic = __shfl_up_sync(kFullMask, ic, CG), nid = __shfl_up_sync(kFullMask, id, CG);
+    take = lane >= CG && nic == ia && nid == ib && (ia >= 0 || ib >= 0);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float ncc = __shfl_up_sync(kFullMask, cc[k], CG), ncd = __shfl_up_sync(kFullMask, cd[k], CG);
+      if (take) {
+        ca[k] += ncc;
+        cb[k] += ncd;
+      }
+    }
+    taken = __shfl_down_sync(kFullMask, (int)take, CG) && lane + CG < 32;
+  }
+  V* o = reinterpret_cast<V*>(out) + base * CG + cg;
+  auto put = [&](int idx, const float* c) {
+    if (idx < 0) return;
+    if (VEC4)
+      atomicAdd(reinterpret_cast<float4*>(o + (size_t)idx * CG), make_float4(c[0], c[VEC4 ? 1 : 0], c[VEC4 ? 2 : 0], c[VEC4 ? 3 : 0]));
+    else
+      atomicAdd(reinterpret_cast<float*>(o + (size_t)idx * CG), c[0]);
+  };
+  put(ia, ca);
+  put(ib, cb);
+  if (!taken) {
+    put(ic, cc);
+    put(id, cd);
   }
 }
 
@@ -206,15 +247,16 @@ extern "C" int uof_splat_fwd(const float* u, const float* flow, float* out, int 
   UOF_REQUIRE(u || C == 1, "splat_fwd: u == NULL (ones) needs C == 1");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long npix = (long long)B * H * W;
-  UOF_REQUIRE(C != 1 || (H <= 65535 && B <= 65535 && (long long)H * W < (1ll << 31)), "splat_fwd: image too large for one launch");
+  UOF_REQUIRE(H <= 65535 && B <= 65535 && (long long)H * W < (1ll << 31) && (long long)W * C < (1ll << 31),
+              "splat_fwd: image too large for one launch");
   UOF_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * C * sizeof(float), stream));
   const float2* f2 = reinterpret_cast<const float2*>(flow);
   if (C == 1) {
     splat1_fwd_kernel<<<dim3(ceil_div(W, 128), H, B), 128, 0, stream>>>(u, f2, out, H, W);
   } else if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(u) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-    splat_fwd_kernel<true><<<(unsigned)ceil_div_ll(npix * (C / 4), 256), 256, 0, stream>>>(u, f2, out, B, H, W, C);
+    splat_fwd_kernel<true><<<dim3((unsigned)ceil_div_ll((long long)W * (C / 4), 256), H, B), 256, 0, stream>>>(u, f2, out, H, W, C, C / 4);
   } else {
-    splat_fwd_kernel<false><<<(unsigned)ceil_div_ll(npix * C, 256), 256, 0, stream>>>(u, f2, out, B, H, W, C);
+    splat_fwd_kernel<false><<<dim3((unsigned)ceil_div_ll((long long)W * C, 256), H, B), 256, 0, stream>>>(u, f2, out, H, W, C, C);
   }
   count_launch(1);
   return check_launch("splat_fwd");
