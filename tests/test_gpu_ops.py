@@ -636,8 +636,8 @@ def test_photo_warp_fused_matches_separate_kernels(U, B, H, W, ac):
     f2 = [f.clone().requires_grad_(True) for f in flows]
     pix2, ssim2, wb2, wf2, warped2 = U.ops.photometric_losses_warped(imgs[1], src, f2, S, ac, return_warped=True)
     g2 = torch.autograd.grad((pix2 * ct[0]).sum() + (ssim2 * ct[1]).sum(), f2)
-    assert_close(pix2, pix1, 2e-6, 'loss_pixel')
-    assert_close(ssim2, ssim1, 2e-6, 'loss_ssim')
+    assert_close(pix2, pix1, 1e-5, 'loss_pixel')          # fp32 atomics: the order of the per-block partial sums varies
+    assert_close(ssim2, ssim1, 1e-5, 'loss_ssim')
     for s in range(S):
         assert torch.equal(warped2[s], warped1[s].detach()), 'warped images differ at level %d' % s
         assert torch.equal(wb2[s], wb1[s]) and torch.equal(wf2[s], wf1[s]), 'weight maps differ at level %d' % s
@@ -718,7 +718,7 @@ def test_flow_loss_pack_matches_separate_nodes(U, B, H, W):
     smooth1 = smooth1[B:] + smooth1[:B]
     for a, b, name in ((pix2, pix1, 'pixel'), (ssim2, ssim1, 'ssim'), (smooth2, smooth1, 'smooth'), (consis2, consis1, 'consis')):
         assert a.shape == b.shape
-        assert_close(a, b, 2e-6, 'loss_' + name)
+        assert_close(a, b, 1e-5, 'loss_' + name)          # fp32 atomics: the order of the per-block partial sums varies
     for s in range(S):
         assert torch.equal(wf2[s], wf1[s]) and torch.equal(wb2[s], wb1[s])
         assert float(g1[s].abs().max()) > 0
