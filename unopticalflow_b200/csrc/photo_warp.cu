@@ -34,7 +34,10 @@ constexpr int kFwdWarps = 4;                // 2 strips x 2 directions
 constexpr int kFwdDepth = 3;                // rows in the forward cp.async ring (the pipeline below assumes 3)
 constexpr int kFwdPlanes = 5;               // img x3, flow x2
 constexpr int kBwdWarps = 6;                // direction x channel
-constexpr int kBwdDepth = 4;
+#ifndef UOF_PW_BWD_DEPTH
+#define UOF_PW_BWD_DEPTH 4
+#endif
+constexpr int kBwdDepth = UOF_PW_BWD_DEPTH;
 constexpr int kBwdSmem = kBwdWarps * (6 * 32 * 16 + kBwdDepth * 3 * 32 * 8 + 10 * 32 * 4) + 2 * 2 * 3 * 3 * 32 * 8;
 
 struct PWParams {
@@ -184,7 +187,9 @@ photo_warp_fwd_kernel(const __grid_constant__ PWParams P, float* __restrict__ su
       dd.y = (fabsf(v[0].y - wv[0].y) + fabsf(v[1].y - wv[1].y) + fabsf(v[2].y - wv[2].y)) * kThird;
       const int par = (r - r_begin) & 1;
       xmine[par * 32] = dd;
+#ifndef UOF_PW_NO_SYNCWARP
       __syncwarp();
+#endif
       named_barrier<64>(bar_id);
       const f2 od = xother[par * 32];
       const float val0 = (wv[0].x == 0.0f && wv[1].x == 0.0f && wv[2].x == 0.0f) ? 0.0f : 1.0f;   // :111-112
@@ -347,7 +352,11 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
     const int pmine = rb + c - 2;
     const bool mine = pout && pmine >= sc.y0 && pmine < sc.y1;
     if (mine) {
+#ifdef UOF_PW_TOP_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int k = 0; k < 2; ++k) {       // not unrolled: 12 instead of 24 64-bit gather addresses live on top of the row state
         const float ix = sample_coord((float)(sc.col + k), k ? fxn.y : fxn.x, W, FLAGS);
         const float iy = sample_coord((float)pmine, k ? fyn.y : fyn.x, H, FLAGS);
@@ -422,7 +431,9 @@ photo_warp_bwd_kernel(const __grid_constant__ PWParams P, const float* __restric
       slot = slot + 1 == kBwdDepth ? 0 : slot + 1;
       gw_s[par][dir][u][c][lane] = gw;
     }
+#ifndef UOF_PW_NO_SYNCWARP
     __syncwarp();
+#endif
     named_barrier<96>(dir);      // the three channel warps of this direction have left their gW of rows rb-2 .. rb
     cp_async_wait<3>();              // the three row groups of this triple may still be in flight, the gathers have landed
     if (mine) {
