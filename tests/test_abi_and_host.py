@@ -89,6 +89,35 @@ def test_no_cpu_fallback():
         u.SSIM(x, x)
 
 
+def test_round2_host_ops_without_gpu():
+    """The round-2 host entry points refuse CPU tensors like every other operator (no fallback), and train.total_loss keeps
+    its torch form for CPU loss packs (the gloo tests and the oracle use it)."""
+    import unopticalflow_b200 as u
+    from unopticalflow_b200 import train
+    img = [torch.zeros(1, 3, 8, 8)]
+    src = [torch.zeros(2, 3, 8, 8)]
+    flo = [torch.zeros(2, 2, 8, 8)]
+    for fn in (u.ops.photometric_losses_warped, u.ops.flow_loss_pack):
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            fn(img, src, flo, 1)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        u.ops.weighted_mean_sum([torch.zeros(4)], [1.0])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        u.ops.upsample_bilinear_scaled(torch.zeros(1, 2, 4, 4), (8, 8), 2.0)
+    pack = {'loss_pixel': torch.tensor([1.0, 3.0]), 'loss_ssim': torch.tensor([2.0, 2.0])}
+    assert float(train.total_loss(pack, {'loss_pixel': 0.5, 'loss_ssim': 2.0})) == pytest.approx(0.5 * 2.0 + 2.0 * 2.0)
+    a, b = u.ops.split_at(torch.arange(12.0).view(6, 2).requires_grad_(True), 4)
+    assert a.shape == (4, 2) and b.shape == (2, 2)
+    x = torch.arange(12.0).view(6, 2).requires_grad_(True)
+    a, b = u.ops.split_at(x, 4)
+    (a.sum() * 2.0 + b.sum() * 3.0).backward()
+    assert torch.equal(x.grad, torch.tensor([[2.0, 2.0]] * 4 + [[3.0, 3.0]] * 2))
+    x = torch.arange(12.0).view(6, 2).requires_grad_(True)
+    a, _ = u.ops.split_at(x, 4)
+    a.sum().backward()                                  # the unused part gets a zero gradient
+    assert torch.equal(x.grad, torch.tensor([[1.0, 1.0]] * 4 + [[0.0, 0.0]] * 2))
+
+
 def test_warp_flow_shape_error_matches_reference():
     import unopticalflow_b200 as u
     with pytest.raises(ValueError, match='the shape of grid .* is not equal to the shape of flow'):
