@@ -250,15 +250,17 @@ bool launch_staged(const float* gout, long long gout_bs, const float* f1, long l
   const int Wp = ceil_div(W, PX) * PX, groups = 256 / nq_pad, cpc = groups * CT, nbands = ceil_div(H, BH);
   const size_t smem = ((size_t)ND * ND * BH * Wp + (size_t)cpc * (BH + 2 * RAD) * (Wp + 2 * RAD)) * sizeof(float);
   if (smem > 200 * 1024) return false;
-  static size_t configured = 0;        // per instantiation
-  if (smem > configured) {
+  static size_t configured[64] = {};   // per instantiation and device (the attribute is per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || smem > configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(cost_volume_bwd_staged_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cost_volume_bwd (staged): %s", cudaGetErrorString(e));
       *rc = UOF_ERR_CUDA;
       return true;
     }
-    configured = smem;
+    if (dev >= 0) configured[dev] = smem;
   }
   cost_volume_bwd_staged_kernel<CT><<<dim3(ceil_div(C, cpc), 2 * nbands, B), 256, smem, stream>>>(
       gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, C, H, W, BH, nbands, nq_pad, 1.0f / (float)C);

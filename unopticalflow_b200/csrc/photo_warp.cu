@@ -517,12 +517,22 @@ int launch_fwd(PWParams& P, const uof_photo_warp_level* levels, int nlevels, int
   return UOF_OK;
 }
 
-// opt in to > 48 KB of dynamic shared memory (once per instantiation) and return the resident blocks per SM
+// opt in to > 48 KB of dynamic shared memory (a per-device attribute: done once per device a kernel is launched on)
+template <class K>
+void bwd_opt_in(K kernel) {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !done[dev]) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess) (void)cudaGetLastError();
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+}
+// resident blocks per SM (for the strip table's wave model)
 template <class K>
 int bwd_occupancy(K kernel) {
   int n = 0;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBwdWarps * 32, kBwdSmem) != cudaSuccess || n < 1) {
+  bwd_opt_in(kernel);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBwdWarps * 32, kBwdSmem) != cudaSuccess || n < 1) {
     (void)cudaGetLastError();
     n = 2;
   }
@@ -537,10 +547,10 @@ int launch_bwd(PWParams& P, const uof_photo_warp_level* levels, int nlevels, int
   if (int rc = fill_params(P, levels, nlevels, B, true, occ[flags])) return rc;
   const int blocks = P.T.warp_begin[nlevels];
   switch (flags) {
-    case 0: photo_warp_bwd_kernel<0, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
-    case 1: photo_warp_bwd_kernel<1, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
-    case 2: photo_warp_bwd_kernel<2, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
-    default: photo_warp_bwd_kernel<3, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    case 0: bwd_opt_in(photo_warp_bwd_kernel<0, MINB>); photo_warp_bwd_kernel<0, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    case 1: bwd_opt_in(photo_warp_bwd_kernel<1, MINB>); photo_warp_bwd_kernel<1, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    case 2: bwd_opt_in(photo_warp_bwd_kernel<2, MINB>); photo_warp_bwd_kernel<2, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
+    default: bwd_opt_in(photo_warp_bwd_kernel<3, MINB>); photo_warp_bwd_kernel<3, MINB><<<blocks, kBwdWarps * 32, kBwdSmem, stream>>>(P, sums, gp, gs); break;
   }
   return UOF_OK;
 }
