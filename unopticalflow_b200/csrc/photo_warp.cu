@@ -517,15 +517,11 @@ int launch_fwd(PWParams& P, const uof_photo_warp_level* levels, int nlevels, int
   return UOF_OK;
 }
 
-// opt in to > 48 KB of dynamic shared memory (a per-device attribute: done once per device a kernel is launched on)
+// opt in to > 48 KB of dynamic shared memory: a per-device, per-function attribute, set before every launch like the
+// cost-volume kernels do (a host-side call of ~1 us; a cache keyed by the function TYPE would conflate the instantiations)
 template <class K>
 void bwd_opt_in(K kernel) {
-  static bool done[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !done[dev]) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess) (void)cudaGetLastError();
-    if (dev >= 0 && dev < 64) done[dev] = true;
-  }
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess) (void)cudaGetLastError();
 }
 // resident blocks per SM (for the strip table's wave model)
 template <class K>
