@@ -572,11 +572,15 @@ def test_photometric_fused_vs_oracle(U, B, H, W):
 
 
 @pytest.mark.parametrize('ac', [False, True])
-@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 40, 72), (2, 16, 136)])
-def test_photo_warp_fused_vs_oracle(U, B, H, W, ac):
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (1, 40, 72), (2, 16, 136), (1, 8, 8), (1, 12, 264)])
+def test_photo_warp_fused_vs_oracle(U, B, H, W, ac, monkeypatch):
     """a3+a4+a5+a6 in one launch each way (uof_photo_warp_loss_*): image warps with validity mask evaluated inside the
     photometric kernels, against the CPU oracle chain warp_flow -> diff_weight -> loss_with_mask / loss_ssim
-    (model_flow_paper.py:236-245): losses, weight / diff maps, the warped images and d loss / d flow."""
+    (model_flow_paper.py:236-245): losses, weight / diff maps, the warped images and d loss / d flow.  The oracle runs on
+    the CPU, so the kernels use ATen's CPU rounding of the coordinate chain (UOF_COORD_HOST): with the CUDA rounding a
+    sample that lands within an ulp of an integer column (here x + fx = 156.000007 at W = 264) takes the neighbouring
+    footprint -- same value, different flow gradient (0.42 relative at that pixel)."""
+    monkeypatch.setattr(U.ops, 'COORD_ARITHMETIC', 'host')
     g = torch.Generator().manual_seed(B * 1000 + H + int(ac))
     S = 3
     pyr, fb, ff, _, _ = pyramid_case(g, B, H, W, S)
@@ -604,7 +608,8 @@ def test_photo_warp_fused_vs_oracle(U, B, H, W, ac):
         assert_close(gw_f[s], w_f[s], REL_TOL, 'weight_fwd')
         assert_close(gd_b[s], d_b[s], REL_TOL, 'diff_bwd')
         assert_close(gd_f[s], d_f[s], REL_TOL, 'diff_fwd')
-        assert float(ref_g[s].abs().max()) > 0
+        if (H >> s) >= 8:           # (a 2x2 level can be masked out entirely: its reference gradient is then exactly zero)
+            assert float(ref_g[s].abs().max()) > 0
         assert_close(got_g[s], torch.cat((ref_g[s], ref_g[S + s]), 0), REL_TOL, 'd loss / d flow, level %d' % s)
 
 
