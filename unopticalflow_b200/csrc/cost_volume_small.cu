@@ -104,70 +104,92 @@ cost_volume_fwd_small_kernel(const float* __restrict__ f1, long long f1_bs, cons
 //                         gout[-d] at the displaced pixel (zero outside the map), so both roles run the same loop;
 //   Fp[ch][BH + 8][Wp + 8] its channels of the other feature map with a zero halo of 4,
 // with rows padded to whole quads (Wp = 4 ceil(W / 4)), so that every later access is an aligned LDS.128 without bounds
-// checks.  The copies are 4-byte zero-filling cp.async (W % 4 != 0 at these levels), all in flight at once: with plain
-// loads every (displacement, row) iteration of a warp waited for its own load and the staging alone took 40 us.  A thread then owns a quad of 4 adjacent pixels and CT channels: per displacement row 3 CT window loads + 9
+// checks (staging: see the kernel).  A thread then owns a quad of 4 adjacent pixels and CT channels: per displacement row 3 CT window loads + 9
 // coefficient loads (LDS.128) feed 36 CT FMAs.  No atomics, every output written once, `gadd` folded in.
-constexpr int kColIters = 3;          // staged rows are at most 96 floats wide (W <= 64)
-
-template <int CT>
-__global__ void __launch_bounds__(256)
+template <int CT, int NT, bool VEC>
+__global__ void __launch_bounds__(NT)
 cost_volume_bwd_staged_kernel(const float* __restrict__ gout, long long gout_bs, const float* __restrict__ f1, long long f1_bs,
                               const float* __restrict__ f2, const float* __restrict__ gadd, long long gadd_bs,
                               float* __restrict__ gf1, float* __restrict__ gf2, int C, int H, int W, int BH, int nbands, int nq_pad,
                               float inv_c) {
   extern __shared__ float4 staged_smem[];
   const int Wq = (W + PX - 1) / PX, Wp = Wq * PX, Wf = Wp + 2 * RAD;
-  const int groups = 256 / nq_pad, cpc = groups * CT;      // channels per CTA
+  const int groups = NT / nq_pad, cpc = groups * CT;       // channels per CTA
   float* Gs = reinterpret_cast<float*>(staged_smem);       // [81][BH][Wp]
   float* Fp = Gs + ND * ND * BH * Wp;                      // [cpc][BH + 8][Wf]
   const bool mirror = (int)blockIdx.y >= nbands;
   const int band = (int)blockIdx.y - (mirror ? nbands : 0);
   const int y0 = band * BH, b = blockIdx.z, c0 = (int)blockIdx.x * cpc;
   const size_t plane = (size_t)H * W;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- stage the coefficients: a warp takes whole displacements, lanes run along x (no runtime division in these loops:
-  // the first version decoded a flat (displacement, row) index and spent 14 k instructions per warp on the staging alone)
+  // ---- staging.  Shared memory is zeroed (halo, padding, out-of-map coefficients), then every SOURCE element the CTA needs
+  // is loaded once with plain coalesced loads -- 16-byte ones when the CTA covers whole images whose planes are multiples
+  // of 4 floats, because then the 81 coefficient planes / the CTA's channel planes are one contiguous block -- and
+  // scattered to its padded (role 1: flipped and shifted) position.  (4-byte cp.async staging was measured at ~2 elements
+  // per clock and SM: 12 of the kernel's 18 us at 4x13.)
+  {
+    float4* z = staged_smem;
+    const int total4 = (ND * ND * BH * Wp + cpc * (BH + 2 * RAD) * Wf) / 4;
+    for (int i = threadIdx.x; i < total4; i += NT) z[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  __syncthreads();
   const float* gb = gout + (size_t)b * gout_bs;
-  for (int d = warp; d < ND * ND; d += 8) {
-    const int i = d / ND, j = d - i * ND;
-    // role 1: coefficient of displacement (i, j) at pixel q is gout[(8 - i, 8 - j)] at q + (i - 4, j - 4)
-    const int xs = mirror ? j - RAD : 0, yo = mirror ? i - RAD : 0;
-    const float* dsrc = gb + (size_t)(mirror ? (ND - 1 - i) * ND + (ND - 1 - j) : d) * plane + xs;
-    float* dst = Gs + (size_t)d * BH * Wp;
-    for (int y = 0; y < BH; ++y, dst += Wp) {
-      const int ys = y0 + y + yo;
-      const bool row_ok = ys >= 0 && ys < H && y0 + y < H;
-      const float* src = dsrc + (size_t)min(max(ys, 0), H - 1) * W;
-#pragma unroll
-      for (int t = 0; t < kColIters; ++t) {                  // a lane owns columns lane, lane + 32, lane + 64 (Wp <= 64 + 8)
-        const int x = lane + 32 * t;
-        const bool ok = row_ok && x < W && x + xs >= 0 && x + xs < W;
-        if (x < Wp) cp_async_4(dst + x, ok ? src + x : gb, ok);   // asynchronous, zero-filled: all copies of a CTA in flight at once
-      }
-    }
-  }
-  // ---- stage the feature rows with their zero halo: a warp takes whole channels
-  const float* fsrc = mirror ? f1 + (size_t)b * f1_bs : f2 + (size_t)b * C * plane;
+  const float* fsrc = (mirror ? f1 + (size_t)b * f1_bs : f2 + (size_t)b * C * plane) + (size_t)c0 * plane;
   const int frows = BH + 2 * RAD;
-  for (int cc = warp; cc < cpc; cc += 8) {
-    const bool c_ok = c0 + cc < C;
-    const float* csrc = fsrc + (size_t)min(c0 + cc, C - 1) * plane - RAD;
-    float* dst = Fp + (size_t)cc * frows * Wf;
-    for (int r = 0; r < frows; ++r, dst += Wf) {
-      const int yy = y0 - RAD + r;
-      const bool row_ok = c_ok && yy >= 0 && yy < H;
-      const float* src = csrc + (size_t)min(max(yy, 0), H - 1) * W;
-#pragma unroll
-      for (int t = 0; t < kColIters; ++t) {
-        const int k = lane + 32 * t;
-        const bool ok = row_ok && k >= RAD && k < W + RAD;
-        if (k < Wf) cp_async_4(dst + k, ok ? src + k : fsrc, ok);
+  const int iplane = H * W;
+  // (plane, row, column) of a flat element index are decoded once per load and advanced incrementally for the following
+  // elements of a vector: the divisions of a per-element decode were most of the staging instructions
+  struct Pos { int p, y, x; };
+  auto decode = [&](int e) {
+    Pos t;
+    t.p = e / iplane;
+    const int rem = e - t.p * iplane;
+    t.y = rem / W;
+    t.x = rem - t.y * W;
+    return t;
+  };
+  auto advance = [&](Pos& t) {
+    if (++t.x == W) {
+      t.x = 0;
+      if (++t.y == H) {
+        t.y = 0;
+        ++t.p;
       }
     }
+  };
+  auto put_g = [&](const Pos& t, float v) {    // t = (displacement, row, column) of a gout element of this image
+    int dd = t.p, qy = t.y, qx = t.x;
+    if (mirror) {                              // coefficient (i', j') at pixel q is gout[(8 - i', 8 - j')] at q + (i' - 4, j' - 4)
+      const int is = t.p / ND, js = t.p - is * ND;
+      dd = (ND - 1 - is) * ND + (ND - 1 - js);
+      qy = t.y - (ND - 1 - is - RAD);
+      qx = t.x - (ND - 1 - js - RAD);
+    }
+    if (qy >= y0 && qy < y0 + BH && qy < H && qx >= 0 && qx < W) Gs[((size_t)dd * BH + (qy - y0)) * Wp + qx] = v;
+  };
+  auto put_f = [&](const Pos& t, float v) {    // t = (channel of this CTA, row, column)
+    const int r = t.y - (y0 - RAD);
+    if (r >= 0 && r < frows) Fp[((size_t)t.p * frows + r) * Wf + t.x + RAD] = v;
+  };
+  const int nch = min(cpc, C - c0);            // channels of this CTA that exist
+  const int ng = ND * ND * iplane, nf = nch * iplane;
+  if (VEC) {
+    const float4* g4 = reinterpret_cast<const float4*>(gb);
+    const float4* f4 = reinterpret_cast<const float4*>(fsrc);
+    for (int i = threadIdx.x; i < ng / 4; i += NT) {
+      const float4 v = __ldg(g4 + i);
+      Pos t = decode(4 * i);
+      put_g(t, v.x); advance(t); put_g(t, v.y); advance(t); put_g(t, v.z); advance(t); put_g(t, v.w);
+    }
+    for (int i = threadIdx.x; i < nf / 4; i += NT) {
+      const float4 v = __ldg(f4 + i);
+      Pos t = decode(4 * i);
+      put_f(t, v.x); advance(t); put_f(t, v.y); advance(t); put_f(t, v.z); advance(t); put_f(t, v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < ng; i += NT) put_g(decode(i), __ldg(gb + i));
+    for (int i = threadIdx.x; i < nf; i += NT) put_f(decode(i), __ldg(fsrc + i));
   }
-  cp_async_commit();
-  cp_async_wait<0>();
   __syncthreads();
 
   const int q = threadIdx.x % nq_pad, g = threadIdx.x / nq_pad;
@@ -243,18 +265,18 @@ bool fwd_small(const float* f1, long long f1_bs, const float* f2, float* out, in
   return true;
 }
 
-template <int CT>
+template <int CT, int NT, bool VEC>
 bool launch_staged(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
                    long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, int BH, int nq_pad, cudaStream_t stream,
                    int* rc) {
-  const int Wp = ceil_div(W, PX) * PX, groups = 256 / nq_pad, cpc = groups * CT, nbands = ceil_div(H, BH);
+  const int Wp = ceil_div(W, PX) * PX, groups = NT / nq_pad, cpc = groups * CT, nbands = ceil_div(H, BH);
   const size_t smem = ((size_t)ND * ND * BH * Wp + (size_t)cpc * (BH + 2 * RAD) * (Wp + 2 * RAD)) * sizeof(float);
   if (smem > 200 * 1024) return false;
   static size_t configured[64] = {};   // per instantiation and device (the attribute is per device)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || smem > configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cost_volume_bwd_staged_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cost_volume_bwd_staged_kernel<CT, NT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("cost_volume_bwd (staged): %s", cudaGetErrorString(e));
       *rc = UOF_ERR_CUDA;
@@ -262,7 +284,7 @@ bool launch_staged(const float* gout, long long gout_bs, const float* f1, long l
     }
     if (dev >= 0) configured[dev] = smem;
   }
-  cost_volume_bwd_staged_kernel<CT><<<dim3(ceil_div(C, cpc), 2 * nbands, B), 256, smem, stream>>>(
+  cost_volume_bwd_staged_kernel<CT, NT, VEC><<<dim3(ceil_div(C, cpc), 2 * nbands, B), NT, smem, stream>>>(
       gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, C, H, W, BH, nbands, nq_pad, 1.0f / (float)C);
   count_launch();
   *rc = check_launch("cost_volume_bwd (staged)");
@@ -271,26 +293,36 @@ bool launch_staged(const float* gout, long long gout_bs, const float* f1, long l
 
 bool bwd_small(const float* gout, long long gout_bs, const float* f1, long long f1_bs, const float* f2, const float* gadd,
                long long gadd_bs, float* gf1, float* gf2, int B, int C, int H, int W, cudaStream_t stream, int* rc) {
-  // Measured (B200, kernel_bench, round 2): 18.6 us at 16x196x4x13 against 25.2 us for the tiled kernels, but 24.1 vs 20.3 us
-  // at 16x128x8x26 (128 CTAs each staging 146 KB through 4-byte cp.async: the staging, not the 81-tap loop, is the
-  // time) and 51 vs 24 us at 16x52 in bands of 4 rows (gout re-staged once per channel chunk).  Default: images of at most
-  // kStagedQuads quads, i.e. the 4x13 level; UOF_CV_BWD_SMALL_MAXQ raises the limit (the larger forms stay parity-tested),
+  // Measured (B200, kernel_bench, round 2): 11.3 us at 16x196x4x13 against 25.2 us for the tiled kernels (18.6 us while the
+  // staging still went through 4-byte cp.async), but 21.7 vs 20.0 us at 16x128x8x26 -- there the 81-tap loop itself is
+  // shared-memory bound (2.3 B of LDS per FMA at 4 channels per thread against 1.5 in the tiled kernels) -- and far slower at
+  // 16x52 in bands of rows (every band CTA re-stages the coefficient planes).  Default: images of at most kStagedQuads
+  // quads, i.e. the 4x13 level; UOF_CV_BWD_SMALL_MAXQ raises the limit (the larger forms stay parity-tested),
   // UOF_CV_NO_SMALL_BWD=1 keeps the tiled kernels everywhere.
   constexpr int kStagedQuads = 16;
   static const bool off = getenv("UOF_CV_NO_SMALL_BWD") != nullptr;
   static const int maxq = getenv("UOF_CV_BWD_SMALL_MAXQ") ? atoi(getenv("UOF_CV_BWD_SMALL_MAXQ")) : kStagedQuads;
   const int qpr = ceil_div(W, PX);
   const long long nq_img = (long long)qpr * H;
-  if (off || nq_img > maxq || qpr > 16 || B > 65535) return false;      // W <= 64: kColIters column passes per staged row
+  if (off || nq_img > maxq || B > 65535 || (long long)ND * ND * H * W >= (1ll << 30) || (long long)C * H * W >= (1ll << 30)) return false;
   // band height: the whole image when it has <= 64 quads, else the most rows that give <= 64 quads
   int BH = H;
   while ((long long)BH * qpr > 64 && BH > 1) BH = (BH + 1) / 2;
   const int nq = BH * qpr;
   int nq_pad = 16;
   while (nq_pad < nq) nq_pad *= 2;
-  // few quads (many thread groups): 4 channels per thread; a full 64-quad band: 8, which halves the re-reads of gout
-  if (nq_pad >= 64) return launch_staged<8>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, BH, nq_pad, stream, rc);
-  return launch_staged<4>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, BH, nq_pad, stream, rc);
+  // Both phases of the kernel (issuing the staging copies, the 81-tap loop) are latency bound with one CTA per SM, so the
+  // CTA has 16 warps; channels per thread: 2 when an image has few quads (many thread groups), 4 for a full 64-quad band
+  // (UOF_CV_STAGED_WIDE=1: the first form, 8 warps with 4 / 8 channels per thread)
+  static const bool wide = getenv("UOF_CV_STAGED_WIDE") != nullptr;
+  // 16-byte staging loads: the CTA covers whole images and every plane / batch stride / base pointer is 16-byte aligned
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2);
+  const bool vec = BH == H && ((long long)H * W) % 4 == 0 && gout_bs % 4 == 0 && f1_bs % 4 == 0 && (bits & 15u) == 0;
+#define UOF_STAGED(CT_, NT_) (vec ? launch_staged<CT_, NT_, true>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, BH, nq_pad, stream, rc) \
+                                  : launch_staged<CT_, NT_, false>(gout, gout_bs, f1, f1_bs, f2, gadd, gadd_bs, gf1, gf2, B, C, H, W, BH, nq_pad, stream, rc))
+  if (wide) return nq_pad >= 64 ? UOF_STAGED(8, 256) : UOF_STAGED(4, 256);
+  return nq_pad >= 64 ? UOF_STAGED(4, 512) : UOF_STAGED(2, 512);
+#undef UOF_STAGED
 }
 
 }  // namespace cv
