@@ -781,6 +781,31 @@ def test_losses_golden_from_reference_fused_warp(U):
         assert_close(grads[s][B:], g['gff%d' % s], REL_TOL, 'grad flow fwd %d' % s)
 
 
+def test_losses_wide_golden_from_reference_loss_pack(U, monkeypatch):
+    """tests/golden/losses_wide.npz (recorded from the unmodified reference on a 16 x 200 frame with decoder-like flows:
+    several 60-column strips, a partial last one, an out-of-bounds column and row) through the one-node loss pack
+    (ops.flow_loss_pack: fused warp + photometric launch, smoothness and consistency accumulating into one gradient
+    buffer).  The fixture comes from the CPU, hence the CPU rounding of the coordinate chain."""
+    monkeypatch.setattr(U.ops, 'COORD_ARITHMETIC', 'host')
+    g = load_golden('losses_wide.npz')
+    S = 3
+    B = g['img'].shape[0]
+    pyr = [U.ops.img_pyramid(g[k].cuda(), 4) for k in ('imgl', 'img', 'imgr')]
+    fl = [torch.cat((g['fb%d' % s], g['ff%d' % s]), 0).cuda().requires_grad_(True) for s in range(S)]
+    src = [torch.cat((pyr[0][s], pyr[2][s]), 0) for s in range(S)]
+    pix, ssim, smooth, consis, w_b, w_f = U.ops.flow_loss_pack(pyr[1], src, fl, S)
+    pack = [pix, ssim, smooth, consis]
+    total = sum((p * c.cuda()).sum() for p, c in zip(pack, g['cts']))
+    grads = torch.autograd.grad(total, fl)
+    for k, name in enumerate(('loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis')):
+        assert_close(pack[k], g[name], REL_TOL, name)
+    for s in range(S):
+        assert_close(w_b[s], g['wb%d' % s], REL_TOL)
+        assert_close(w_f[s], g['wf%d' % s], REL_TOL)
+        assert_close(grads[s][:B], g['gfb%d' % s], REL_TOL, 'grad flow bwd %d' % s)
+        assert_close(grads[s][B:], g['gff%d' % s], REL_TOL, 'grad flow fwd %d' % s)
+
+
 def test_photo_warp_odd_width_takes_separate_kernels(U):
     """Levels with odd W cannot use the pixel-pair kernels: the host op falls back to uof_warp_* + uof_photo_loss_* (still
     CUDA) and the C ABI says UOF_ERR_UNSUPPORTED rather than computing something else."""

@@ -97,6 +97,19 @@ def test_losses_golden():
         assert_close(w_f[s], g['wf%d' % s], TOL)
 
 
+def test_losses_wide_golden():
+    """The same chain on the wide-frame fixture (oracle/make_golden_wide.py: 16 x 200, decoder-like flows)."""
+    g = load_golden('losses_wide.npz')
+    pack, grads, w_b, w_f = oracle_losses(g)
+    for k, name in enumerate(('loss_pixel', 'loss_ssim', 'loss_flow_smooth', 'loss_flow_consis')):
+        assert_close(pack[k], g[name], TOL, name)
+    for s in range(3):
+        assert_close(grads[s], g['gfb%d' % s], TOL)
+        assert_close(grads[3 + s], g['gff%d' % s], TOL)
+        assert_close(w_b[s], g['wb%d' % s], TOL)
+        assert_close(w_f[s], g['wf%d' % s], TOL)
+
+
 def test_step_golden():
     for tag, (B, H, W) in {'b1_64x128': (1, 64, 128), 'b2_64x64': (2, 64, 64), 'b1_256x832': (1, 256, 832)}.items():
         g = load_golden('step_%s.npz' % tag)
