@@ -71,6 +71,66 @@ def test_argument_validation_without_gpu(lib):
         _lib.call('uof_photo_warp_loss_bwd', lv, 1, 1, 0, P, P, P, None)
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every ctypes prototype in _lib.SIGNATURES lists as many arguments as the declaration in include/uof_b200.h, and
+    pointer / integer / float kinds agree position by position."""
+    from unopticalflow_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'uof_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = dict(re.findall(r'\bint\s+(uof_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;', text, flags=re.S))
+    assert len(decls) >= 40
+
+    def kind_of_c(param):
+        p = ' '.join(param.split())
+        if '*' in p or 'uof_stream_t' in p:
+            return 'ptr'
+        if p.startswith('float') or ' float ' in ' ' + p + ' ':
+            return 'float'
+        return 'int'
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_float, ctypes.c_double):
+            return 'float'
+        if t in (ctypes.c_int, ctypes.c_longlong):
+            return 'int'
+        return 'ptr'
+
+    for name, argtypes in _lib.SIGNATURES.items():
+        params = [p for p in decls[name].split(',') if p.strip() and p.strip() != 'void']
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (p, t) in enumerate(zip(params, argtypes)):
+            assert kind_of_c(p) == kind_of_ctypes(t), (name, i, p.strip(), t)
+
+
+def test_level_structs_match_the_header(tmp_path):
+    """The ctypes mirrors of the per-level structs (_lib.PhotoLevel, PhotoWarpLevel, SmoothLevel, ConsisLevel) have the
+    size and field offsets a C compiler gives the structs of include/uof_b200.h (plain C: the header must also compile as C)."""
+    import shutil
+    import subprocess
+    from unopticalflow_b200 import _lib
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no C compiler')
+    pairs = {'uof_photo_level': _lib.PhotoLevel, 'uof_photo_warp_level': _lib.PhotoWarpLevel,
+             'uof_smooth_level': _lib.SmoothLevel, 'uof_consis_level': _lib.ConsisLevel}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "uof_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split('\n')
+    got = {l.split()[0]: [int(v) for v in l.split()[1:]] for l in out if l.strip()}
+    for cname, cls in pairs.items():
+        want = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert got[cname] == want, (cname, got[cname], want)
+
+
 def test_library_missing_fails_loudly(tmp_path, monkeypatch):
     from unopticalflow_b200 import _lib
     monkeypatch.setattr(_lib, '_lib', None)
